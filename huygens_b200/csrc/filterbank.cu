@@ -1,0 +1,338 @@
+// filterbank.cu — Filterbank<T> / FFilterbank<T,N,order> tick loop on sm_100a.
+//
+// Replaces /root/reference/src/filterbank.h:170-187 (compute), :125-139 (operator()), :142-148
+// (tick) for whole blocks of samples.  Two time strategies:
+//   K1 "exact": one register-resident lane per (stream, filter); serial in time; every operation
+//       of compute() is replayed with the oracle's rounding sequence, so y_n[t] is bit-identical
+//       to the reference loop.  Only the N-way mixdown order differs (warp/CTA tree).
+//   K2 "scan":  see filterbank_scan.cu.
+#include <cuda_pipeline.h>
+#include "hg_common.cuh"
+#include "filterbank_handle.cuh"
+
+namespace hg {
+
+// ---------------------------------------------------------------------------------------------
+// K1 kernel
+//   grid  = (filter groups, streams); CTA = NT threads; thread owns F filters
+//           n = group*NT*F + k*NT + tid  (k < F) of one stream.
+//   smem  = input chunk xs[2][XT] (cp.async double buffer, broadcast reads) +
+//           partial sums red[2][TILE][NT+NW] (transposed CTA reduction, conflict-free).
+//   The smoothed gains p, g are one-pole recursions towards constant targets; once they reach
+//   their floating-point fixed point (p == fl(fl(c*pin) + fl(s*p))) they never change again, so
+//   the CTA drops to a loop without them.  That is bit-exact, not an approximation.
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_TILE = 32;
+constexpr int K1_XT = 1024;
+
+template <typename T> struct Vec4 { T v[4]; };
+
+template <typename T> __device__ __forceinline__ void lds4(const T* p, T (&x)[4]);
+template <> __device__ __forceinline__ void lds4<float>(const float* p, float (&x)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+template <> __device__ __forceinline__ void lds4<double>(const double* p, double (&x)[4]) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *reinterpret_cast<const double2*>(p + 2);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void stg4(T* p, const T (&y)[4]);
+template <> __device__ __forceinline__ void stg4<float>(float* p, const float (&y)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
+}
+template <> __device__ __forceinline__ void stg4<double>(double* p, const double (&y)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(y[0], y[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(y[2], y[3]);
+}
+
+template <typename T, int F> struct Lane {
+    T b0[F], b1[F], b2[F], a1[F], a2[F];
+    T y1[F], y2[F], p[F], g[F], cp[F], cg[F];
+};
+
+// one sample for the F filters of this thread; returns sum_f y_f * g_f
+template <typename T, bool FMA, int F, bool SMOOTH, bool BANDS>
+__device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T s_g, T (&yb)[F]) {
+    typedef Ar<T, FMA> A;
+    T acc = (T)0;
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        if (SMOOTH) {                                    // filterbank.h:172-173
+            r.p[f] = A::muladd(s_p, r.p[f], r.cp[f]);
+            r.g[f] = A::muladd(s_g, r.g[f], r.cg[f]);
+        }
+        T fw = A::mul(r.b0[f], x0);                      // :178  GEMV over the 3 taps
+        fw = A::muladd(r.b1[f], x1, fw);
+        fw = A::muladd(r.b2[f], x2, fw);
+        T fb = A::mul(r.a1[f], r.y1[f]);                 // :179  feedback dot
+        fb = A::muladd(r.a2[f], r.y2[f], fb);
+        T y = A::mulsub(fw, r.p[f], fb);                 // :178-179  fw .* p - fb
+        r.y2[f] = r.y1[f];
+        r.y1[f] = y;
+        if (BANDS) yb[f] = y;
+        acc = A::acc(y, r.g[f], acc);                    // :130  row . gains_out
+    }
+    return acc;
+}
+
+template <typename T, bool FMA, int F, int NT, bool BANDS>
+__global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
+    typedef Ar<T, FMA> A;
+    constexpr int NW = NT / 32;
+    constexpr int RS = NT + NW;          // row stride == NW (mod 32): STS and reduce both conflict-free
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);          // [2][XT]
+    T* red = xs + 2 * K1_XT;                          // [2][TILE][RS]
+
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x, s = blockIdx.y;
+    const int N = P.N;
+    const long L = P.L;
+    const int n_base = grp * NT * F;
+
+    Lane<T, F> r;
+    const size_t SN = (size_t)P.S * N;
+    bool conv = true;
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        const int n = n_base + f * NT + tid;
+        const bool ok = n < N;
+        r.b0[f] = ok ? P.par[0 * (size_t)N + n] : (T)0;
+        r.b1[f] = ok ? P.par[1 * (size_t)N + n] : (T)0;
+        r.b2[f] = ok ? P.par[2 * (size_t)N + n] : (T)0;
+        r.a1[f] = ok ? P.par[3 * (size_t)N + n] : (T)0;
+        r.a2[f] = ok ? P.par[4 * (size_t)N + n] : (T)0;
+        const T pin = ok ? P.par[5 * (size_t)N + n] : (T)0;
+        const T gin = ok ? P.par[6 * (size_t)N + n] : (T)0;
+        const size_t si = (size_t)s * N + n;
+        r.y1[f] = ok ? P.state[0 * SN + si] : (T)0;
+        r.y2[f] = ok ? P.state[1 * SN + si] : (T)0;
+        r.p[f] = ok ? P.state[2 * SN + si] : (T)0;
+        r.g[f] = ok ? P.state[3 * SN + si] : (T)0;
+        r.cp[f] = A::mul(P.c_p, pin);                    // fl((1-s)*pin) is loop invariant
+        r.cg[f] = A::mul(P.c_g, gin);
+        conv = conv && (A::muladd(P.s_p, r.p[f], r.cp[f]) == r.p[f]) &&
+               (A::muladd(P.s_g, r.g[f], r.cg[f]) == r.g[f]);
+    }
+    T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
+
+    const T* inp = P.in + (size_t)s * P.in_stride;
+    const long nchunks = (L + K1_XT - 1) / K1_XT;
+    auto stage = [&](long c) {
+        const long base = c * K1_XT;
+        const int cnt = (int)min((long)K1_XT, L - base);
+        T* dst = xs + (c & 1) * K1_XT;
+        for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, inp + base + i, sizeof(T));
+        __pipeline_commit();
+    };
+    if (nchunks > 0) stage(0);
+
+    T* out_row = P.direct ? (P.out + (size_t)s * P.out_stride)
+                          : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
+    long tile_idx = 0;
+    int all_conv = 0;
+    for (long c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) {
+            stage(c + 1);
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        all_conv = __syncthreads_and(conv);
+        const int cnt = (int)min((long)K1_XT, L - c * K1_XT);
+        const T* xc = xs + (c & 1) * K1_XT;
+        for (int t0 = 0; t0 < cnt; t0 += K1_TILE, tile_idx++) {
+            const int tn = min(K1_TILE, cnt - t0);
+            T* rb = red + (tile_idx & 1) * (K1_TILE * RS);
+            const long tg = c * K1_XT + t0;          // time index of the tile start in this block
+            int tt = 0;
+            T yb[F][4];
+            T ybs[F];
+            if (all_conv) {
+                for (; tt + 4 <= tn; tt += 4) {
+                    T xv[4];
+                    lds4<T>(xc + t0 + tt, xv);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        T acc = k1_sample<T, FMA, F, false, BANDS>(r, xv[k], x1, x2, P.s_p, P.s_g, ybs);
+                        x2 = x1; x1 = xv[k];
+                        rb[(tt + k) * RS + tid] = acc;
+                        if (BANDS) {
+#pragma unroll
+                            for (int f = 0; f < F; f++) yb[f][k] = ybs[f];
+                        }
+                    }
+                    if (BANDS) {
+#pragma unroll
+                        for (int f = 0; f < F; f++) {
+                            const int n = n_base + f * NT + tid;
+                            if (n < N) {
+                                T* bp = P.bands + ((size_t)s * N + n) * P.bands_stride + tg + tt;
+                                if (P.bands_vec) stg4<T>(bp, yb[f]);
+                                else { bp[0] = yb[f][0]; bp[1] = yb[f][1]; bp[2] = yb[f][2]; bp[3] = yb[f][3]; }
+                            }
+                        }
+                    }
+                }
+                for (; tt < tn; tt++) {
+                    const T x0 = xc[t0 + tt];
+                    T acc = k1_sample<T, FMA, F, false, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs);
+                    x2 = x1; x1 = x0;
+                    rb[tt * RS + tid] = acc;
+                    if (BANDS) {
+#pragma unroll
+                        for (int f = 0; f < F; f++) {
+                            const int n = n_base + f * NT + tid;
+                            if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
+                        }
+                    }
+                }
+            } else {
+                for (; tt < tn; tt++) {
+                    const T x0 = xc[t0 + tt];
+                    T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs);
+                    x2 = x1; x1 = x0;
+                    rb[tt * RS + tid] = acc;
+                    if (BANDS) {
+#pragma unroll
+                        for (int f = 0; f < F; f++) {
+                            const int n = n_base + f * NT + tid;
+                            if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
+                        }
+                    }
+                }
+                conv = true;
+#pragma unroll
+                for (int f = 0; f < F; f++)
+                    conv = conv && (A::muladd(P.s_p, r.p[f], r.cp[f]) == r.p[f]) &&
+                           (A::muladd(P.s_g, r.g[f], r.cg[f]) == r.g[f]);
+            }
+            all_conv = __syncthreads_and(conv);
+            // transposed reduction of the tile: warp w owns samples [w*SPW, (w+1)*SPW); NW lanes
+            // per sample, each summing 32 of the NT per-thread partials, then a shuffle tree.
+            if (P.out) cta_tile_reduce<T, NT>(rb, tn, out_row + tg);
+        }
+    }
+    // state write-back
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        const int n = n_base + f * NT + tid;
+        if (n < N) {
+            const size_t si = (size_t)s * N + n;
+            P.state[0 * SN + si] = r.y1[f];
+            P.state[1 * SN + si] = r.y2[f];
+            P.state[2 * SN + si] = r.p[f];
+            P.state[3 * SN + si] = r.g[f];
+        }
+    }
+    if (grp == 0 && tid == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+}
+
+// out[s][t] = sum_g partial[g][s][t], fixed order -> deterministic
+template <typename T>
+__global__ void __launch_bounds__(256) fb_reduce_partials(const T* __restrict__ partial, T* __restrict__ out,
+                                                          int groups, int S, long L, long out_stride) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= L) return;
+    T sum = (T)0;
+    for (int g = 0; g < groups; g++) sum += partial[((size_t)g * S + s) * (size_t)L + i];
+    out[(size_t)s * out_stride + i] = sum;
+}
+
+template <typename T, bool FMA, int F, int NT, bool BANDS>
+static hg_status launch_k1(const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    constexpr int NW = NT / 32;
+    const size_t smem = sizeof(T) * (2 * K1_XT + 2 * K1_TILE * (NT + NW));
+    auto kern = fb_exact_kernel<T, FMA, F, NT, BANDS>;
+    if (smem > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(groups, P.S), NT, smem, st>>>(P);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}
+
+template <typename T, bool FMA, int NT, bool BANDS>
+static hg_status launch_k1_F(int F, const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    switch (F) {
+        case 1: return launch_k1<T, FMA, 1, NT, BANDS>(P, groups, st);
+        case 2: return launch_k1<T, FMA, 2, NT, BANDS>(P, groups, st);
+        case 4: return launch_k1<T, FMA, 4, NT, BANDS>(P, groups, st);
+        case 8: return launch_k1<T, FMA, 8, NT, BANDS>(P, groups, st);
+    }
+    return fail(HG_ERR_INVALID, "bad F %d", F);
+}
+
+// choose filters-per-thread so that the grid covers the SMs; more filters per thread amortise the
+// per-sample reduction overhead, fewer expose more lanes.
+static void k1_config(const hg_fb* fb, int* F_out, int* groups_out) {
+    const long lanes = (long)fb->N * fb->S;
+    const long smsp_threads = (long)fb->sm_count * 4 * 32;   // one warp per scheduler
+    int F = 1;
+    if (fb->force_F > 0) F = fb->force_F;
+    else if (lanes >= smsp_threads * 8 * 2) F = 8;
+    else if (lanes >= smsp_threads * 4) F = 4;
+    else if (lanes >= smsp_threads * 2) F = 2;
+    // a single stream cannot use more filters/thread than fills one group sensibly
+    while (F > 1 && fb->N < K1_NT * F / 2) F >>= 1;
+    *F_out = F;
+    *groups_out = (fb->N + K1_NT * F - 1) / (K1_NT * F);
+}
+
+template <typename T>
+hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st) {
+    int F, groups;
+    k1_config(fb, &F, &groups);
+    fb->last_F = F;
+    fb->last_ctas = groups * fb->S;
+    // segment the block so the partial-sum scratch stays bounded
+    size_t seg = L;
+    if (groups > 1 && d_out) {
+        const size_t budget = (size_t)256 << 20;
+        size_t per_sample = (size_t)groups * fb->S * sizeof(T);
+        size_t max_seg = budget / per_sample;
+        max_seg = max_seg < 4096 ? 4096 : (max_seg / 1024) * 1024;
+        if (seg > max_seg) seg = max_seg;
+        HG_TRY(fb->partial.reserve((size_t)groups * fb->S * seg * sizeof(T)));
+    }
+    const bool vec_ok = d_bands && (((uintptr_t)d_bands) % 16 == 0) && (L % 4 == 0);
+    for (size_t t0 = 0; t0 < L; t0 += seg) {
+        const size_t len = (L - t0 < seg) ? (L - t0) : seg;
+        FbK1Params<T> P;
+        P.par = (const T*)fb->d_par;
+        P.state = (T*)fb->d_state;
+        P.xh = (const T*)fb->d_xh + (size_t)fb->xh_cur * 2 * fb->S;          // ping-pong: late CTAs of this
+        P.xh_out = (T*)fb->d_xh + (size_t)(fb->xh_cur ^ 1) * 2 * fb->S;      // launch still read the old history
+        fb->xh_cur ^= 1;
+        P.in = d_in + t0;
+        P.in_stride = (long)L;
+        P.direct = (groups == 1) ? 1 : 0;
+        P.out = d_out ? (P.direct ? d_out + t0 : (T*)fb->partial.p) : nullptr;
+        P.out_stride = (long)L;
+        P.bands = d_bands ? d_bands + t0 : nullptr;
+        P.bands_stride = (long)L;
+        P.bands_vec = (vec_ok && (t0 % 4 == 0)) ? 1 : 0;
+        P.N = fb->N;
+        P.S = fb->S;
+        P.L = (long)len;
+        P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
+        hg_status rc;
+        const bool fma = fb->arith == HG_ARITH_FMA;
+        if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
+        else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
+        HG_TRY(rc);
+        fb->last_launches++;
+        if (!P.direct && d_out) {
+            dim3 grid((unsigned)((len + 255) / 256), fb->S);
+            fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, groups, fb->S, (long)len, (long)L);
+            HG_CUDA(cudaGetLastError());
+            fb->last_launches++;
+        }
+    }
+    return HG_OK;
+}
+
+template hg_status fb_process_exact<float>(hg_fb*, const float*, float*, float*, size_t, cudaStream_t);
+template hg_status fb_process_exact<double>(hg_fb*, const double*, double*, double*, size_t, cudaStream_t);
+
+}  // namespace hg

@@ -1,0 +1,250 @@
+// filterbank_capi.cu — hg_fb_* entry points (see include/huygens_cuda.h for the reference
+// members each one replaces).
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include "hg_common.cuh"
+#include "filterbank_handle.cuh"
+
+namespace {
+
+// /root/reference/src/includes.h:38-48
+double relaxation(double k) {
+    const double order = std::log2(std::numeric_limits<double>::epsilon());
+    if (k == 0) return 0;
+    return std::pow(2.0, order / (std::fmax(0, k) * 48000));
+}
+
+template <typename T> T* par_row(hg_fb* fb, int k) { return (T*)fb->h_par + (size_t)k * fb->N; }
+
+template <typename T>
+hg_status set_rows(hg_fb* fb, int first_row, int max_rows, int n0, int count, const void* src, int n_src) {
+    const T* v = (const T*)src;
+    const int use = n_src < max_rows ? n_src : max_rows;
+    for (int i = 0; i < count; i++)
+        for (int k = 0; k < use; k++) par_row<T>(fb, first_row + k)[n0 + i] = v[(size_t)i * n_src + k];
+    return HG_OK;
+}
+
+hg_status check_range(hg_fb* fb, int n0, int count, const char* what) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "%s: null handle", what);
+    if (count < 0 || n0 < 0 || (long)n0 + count > fb->N)
+        return hg::fail(HG_ERR_INVALID, "%s: filters [%d, %d) out of range [0, %d)", what, n0, n0 + count, fb->N);
+    return HG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filters, int n_streams,
+                       double k_p, double k_g, int flags, int device) {
+    if (!out) return hg::fail(HG_ERR_INVALID, "hg_fb_create: null out");
+    *out = nullptr;
+    if (dtype != HG_F32 && dtype != HG_F64) return hg::fail(HG_ERR_INVALID, "hg_fb_create: bad dtype %d", dtype);
+    if (arith != HG_ARITH_STRICT && arith != HG_ARITH_FMA) return hg::fail(HG_ERR_INVALID, "hg_fb_create: bad arith %d", arith);
+    if (order < 0) return hg::fail(HG_ERR_INVALID, "hg_fb_create: negative order");
+    if (order > 2)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_create: order %d > 2 is not built for the device (every Filterbank in the reference is order 2)", order);
+    if (n_filters < 1 || n_streams < 1) return hg::fail(HG_ERR_INVALID, "hg_fb_create: need n_filters >= 1 and n_streams >= 1");
+    if (hg_device_count() <= device || device < 0)
+        return hg::fail(HG_ERR_CUDA, "hg_fb_create: CUDA device %d not available (%d visible); there is no CPU fallback", device, hg_device_count());
+    HG_CUDA(cudaSetDevice(device));
+    hg_fb* fb = new (std::nothrow) hg_fb();
+    if (!fb) return hg::fail(HG_ERR_NOMEM, "hg_fb_create: host allocation failed");
+    fb->dtype = dtype; fb->arith = arith; fb->order = order; fb->N = n_filters; fb->S = n_streams;
+    fb->flags = flags; fb->device = device;
+    cudaDeviceProp prop;
+    HG_CUDA(cudaGetDeviceProperties(&prop, device));
+    fb->sm_count = prop.multiProcessorCount;
+    const double sp = relaxation(k_p), sg = relaxation(k_g);
+    if (dtype == HG_F32) {
+        float fsp = (float)sp, fsg = (float)sg;
+        fb->s_p = fsp; fb->s_g = fsg;
+        if (flags & HG_FB_FIXED) { fb->c_p = 1.0f - fsp; fb->c_g = 1.0f - fsg; }      // filterbank.h:291,305-306
+        else { fb->c_p = (float)(1 - sp); fb->c_g = (float)(1 - sg); }                 // filterbank.h:165,172-173
+    } else {
+        fb->s_p = sp; fb->s_g = sg; fb->c_p = 1 - sp; fb->c_g = 1 - sg;
+    }
+    const size_t es = hg::dtype_size(dtype);
+    const size_t N = fb->N, S = fb->S;
+    const char* e = getenv("HG_FB_FORCE_F");
+    if (e) fb->force_F = atoi(e);
+    e = getenv("HG_FB_FORCE_CHUNKS");
+    if (e) fb->force_chunks = atoi(e);
+    cudaError_t ce;
+    if ((ce = cudaMallocHost(&fb->h_par, 7 * N * es)) != cudaSuccess ||
+        (ce = cudaMalloc(&fb->d_par, 7 * N * es)) != cudaSuccess ||
+        (ce = cudaMalloc(&fb->d_state, 4 * S * N * es)) != cudaSuccess ||
+        (ce = cudaMalloc(&fb->d_xh, 2 * S * 2 * es)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&fb->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        hg_fb_destroy(fb);
+        return hg::fail(HG_ERR_NOMEM, "hg_fb_create: allocation failed: %s", cudaGetErrorString(ce));
+    }
+    memset(fb->h_par, 0, 7 * N * es);                         // filterbank.h:60-69 setZero
+    HG_CUDA(cudaMemset(fb->d_state, 0, 4 * S * N * es));
+    HG_CUDA(cudaMemset(fb->d_xh, 0, 2 * S * 2 * es));
+    fb->dirty = true;
+    *out = fb;
+    return HG_OK;
+}
+
+hg_status hg_fb_destroy(hg_fb* fb) {
+    if (!fb) return HG_OK;
+    cudaSetDevice(fb->device);
+    if (fb->own_stream) { cudaStreamSynchronize(fb->own_stream); cudaStreamDestroy(fb->own_stream); }
+    if (fb->h_par) cudaFreeHost(fb->h_par);
+    if (fb->d_par) cudaFree(fb->d_par);
+    if (fb->d_state) cudaFree(fb->d_state);
+    if (fb->d_xh) cudaFree(fb->d_xh);
+    fb->in_stage.release(); fb->out_stage.release(); fb->bands_stage.release(); fb->partial.release();
+    fb->scan_a.release(); fb->scan_b.release();
+    delete fb;
+    return HG_OK;
+}
+
+hg_status hg_fb_set_coefficients(hg_fb* fb, int n0, int count, const void* fwd, int n_fwd, const void* back, int n_back) {
+    HG_TRY(check_range(fb, n0, count, "hg_fb_set_coefficients"));
+    if ((n_fwd > 0 && !fwd) || (n_back > 0 && !back) || n_fwd < 0 || n_back < 0)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_set_coefficients: null/negative coefficient arrays");
+    if (fb->dtype == HG_F32) {
+        set_rows<float>(fb, 0, fb->order + 1, n0, count, fwd, n_fwd);
+        set_rows<float>(fb, 3, fb->order, n0, count, back, n_back);
+    } else {
+        set_rows<double>(fb, 0, fb->order + 1, n0, count, fwd, n_fwd);
+        set_rows<double>(fb, 3, fb->order, n0, count, back, n_back);
+    }
+    fb->dirty = true;
+    return HG_OK;
+}
+
+hg_status hg_fb_set_boost(hg_fb* fb, int n0, int count, const void* values) {
+    HG_TRY(check_range(fb, n0, count, "hg_fb_set_boost"));
+    if (count && !values) return hg::fail(HG_ERR_INVALID, "hg_fb_set_boost: null values");
+    if (fb->dtype == HG_F32) set_rows<float>(fb, 5, 1, n0, count, values, 1);
+    else set_rows<double>(fb, 5, 1, n0, count, values, 1);
+    fb->dirty = true;
+    return HG_OK;
+}
+
+hg_status hg_fb_set_mix(hg_fb* fb, int n0, int count, const void* values) {
+    HG_TRY(check_range(fb, n0, count, "hg_fb_set_mix"));
+    if (count && !values) return hg::fail(HG_ERR_INVALID, "hg_fb_set_mix: null values");
+    if (fb->dtype == HG_F32) set_rows<float>(fb, 6, 1, n0, count, values, 1);
+    else set_rows<double>(fb, 6, 1, n0, count, values, 1);
+    fb->dirty = true;
+    return HG_OK;
+}
+
+hg_status hg_fb_open(hg_fb* fb) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_open: null handle");
+    for (int n = 0; n < fb->N; n++) {
+        if (fb->dtype == HG_F32) par_row<float>(fb, 6)[n] = 1.0f;
+        else par_row<double>(fb, 6)[n] = 1.0;
+    }
+    fb->dirty = true;
+    return HG_OK;
+}
+
+hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_bands, size_t L, int mode,
+                        int distortion, void* cuda_stream) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null handle");
+    if (mode != HG_MODE_AUTO && mode != HG_MODE_EXACT && mode != HG_MODE_SCAN)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_process: bad mode %d", mode);
+    if (distortion != HG_DIST_NONE)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: distortion %d not built yet", distortion);
+    fb->last_launches = 0;
+    if (L == 0) return HG_OK;
+    if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
+    if (!out_sum && !out_bands) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
+    HG_CUDA(cudaSetDevice(fb->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : fb->own_stream;
+    const size_t es = hg::dtype_size(fb->dtype);
+    const size_t S = fb->S, N = fb->N;
+
+    if (fb->dirty) {
+        HG_CUDA(cudaMemcpyAsync(fb->d_par, fb->h_par, 7 * N * es, cudaMemcpyHostToDevice, st));
+        // the pinned shadow may be rewritten by a setter right after we return
+        HG_CUDA(cudaStreamSynchronize(st));
+        fb->dirty = false;
+    }
+    const bool in_dev = hg::is_device_ptr(in);
+    const bool out_dev = out_sum ? hg::is_device_ptr(out_sum) : true;
+    const bool bands_dev = out_bands ? hg::is_device_ptr(out_bands) : true;
+    const void* d_in = in;
+    void* d_out = out_sum;
+    void* d_bands = out_bands;
+    if (!in_dev) {
+        HG_TRY(fb->in_stage.reserve(S * L * es));
+        HG_CUDA(cudaMemcpyAsync(fb->in_stage.p, in, S * L * es, cudaMemcpyHostToDevice, st));
+        d_in = fb->in_stage.p;
+    }
+    if (out_sum && !out_dev) {
+        HG_TRY(fb->out_stage.reserve(S * L * es));
+        d_out = fb->out_stage.p;
+    }
+    if (out_bands && !bands_dev) {
+        HG_TRY(fb->bands_stage.reserve(S * N * L * es));
+        d_bands = fb->bands_stage.p;
+    }
+
+    int use = mode;
+    if (use == HG_MODE_AUTO) {
+        // scan only pays when the lanes cannot fill the schedulers and the block is long; it is
+        // not bit-identical, so AUTO keeps fp32 on the exact path.
+        const long lanes = (long)N * S;
+        const bool few = lanes < (long)fb->sm_count * 4 * 32;
+        use = (few && L >= 65536 && fb->dtype == HG_F64 && !out_bands) ? HG_MODE_SCAN : HG_MODE_EXACT;
+    }
+    if (use == HG_MODE_SCAN && out_bands)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: scan mode renders the bank sum only");
+    fb->last_mode = use;
+    hg_status rc;
+    if (use == HG_MODE_EXACT) {
+        rc = fb->dtype == HG_F32 ? hg::fb_process_exact<float>(fb, (const float*)d_in, (float*)d_out, (float*)d_bands, L, st)
+                                 : hg::fb_process_exact<double>(fb, (const double*)d_in, (double*)d_out, (double*)d_bands, L, st);
+    } else {
+        rc = fb->dtype == HG_F32 ? hg::fb_process_scan<float>(fb, (const float*)d_in, (float*)d_out, L, st)
+                                 : hg::fb_process_scan<double>(fb, (const double*)d_in, (double*)d_out, L, st);
+    }
+    HG_TRY(rc);
+    bool need_sync = !in_dev;
+    if (out_sum && !out_dev) { HG_CUDA(cudaMemcpyAsync(out_sum, d_out, S * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
+    if (out_bands && !bands_dev) { HG_CUDA(cudaMemcpyAsync(out_bands, d_bands, S * N * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
+    if (need_sync) HG_CUDA(cudaStreamSynchronize(st));
+    return HG_OK;
+}
+
+hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void* xhist) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_get_state: null handle");
+    HG_CUDA(cudaSetDevice(fb->device));
+    HG_CUDA(cudaDeviceSynchronize());
+    const size_t es = hg::dtype_size(fb->dtype), SN = (size_t)fb->S * fb->N * es;
+    void* dst[4] = {y1, y2, p, g};
+    for (int k = 0; k < 4; k++)
+        if (dst[k]) HG_CUDA(cudaMemcpy(dst[k], (char*)fb->d_state + k * SN, SN, cudaMemcpyDeviceToHost));
+    if (xhist) HG_CUDA(cudaMemcpy(xhist, (char*)fb->d_xh + (size_t)fb->xh_cur * 2 * fb->S * es, 2 * fb->S * es, cudaMemcpyDeviceToHost));
+    return HG_OK;
+}
+
+hg_status hg_fb_set_state(hg_fb* fb, const void* y1, const void* y2, const void* p, const void* g, const void* xhist) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: null handle");
+    HG_CUDA(cudaSetDevice(fb->device));
+    HG_CUDA(cudaDeviceSynchronize());
+    const size_t es = hg::dtype_size(fb->dtype), SN = (size_t)fb->S * fb->N * es;
+    const void* src[4] = {y1, y2, p, g};
+    for (int k = 0; k < 4; k++)
+        if (src[k]) HG_CUDA(cudaMemcpy((char*)fb->d_state + k * SN, src[k], SN, cudaMemcpyHostToDevice));
+    if (xhist) HG_CUDA(cudaMemcpy((char*)fb->d_xh + (size_t)fb->xh_cur * 2 * fb->S * es, xhist, 2 * fb->S * es, cudaMemcpyHostToDevice));
+    return HG_OK;
+}
+
+hg_status hg_fb_last_launch(hg_fb* fb, int* mode_used, int* launches, int* filters_per_thread, int* grid_ctas) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_last_launch: null handle");
+    if (mode_used) *mode_used = fb->last_mode;
+    if (launches) *launches = fb->last_launches;
+    if (filters_per_thread) *filters_per_thread = fb->last_F;
+    if (grid_ctas) *grid_ctas = fb->last_ctas;
+    return HG_OK;
+}
+}

@@ -1,0 +1,53 @@
+// filterbank_handle.cuh — hg_fb handle layout and kernel parameter blocks.
+#pragma once
+#include <cstdint>
+#include "hg_common.cuh"
+
+constexpr int K1_NT = 128;   // threads per CTA of the exact kernel (one warp per SM sub-partition)
+
+// Device layout (all of the handle's dtype T):
+//   d_par   [7][N]      b0 b1 b2 a1 a2 pin gin          (shared by all streams)
+//   d_state [4][S][N]   y1 y2 p g                        (per stream)
+//   d_xh    [2][S][2]   x[t-1], x[t-2] per stream, ping-pong between launches
+struct hg_fb {
+    int dtype, arith, order, N, S, flags, device;
+    int sm_count;
+    double c_p, s_p, c_g, s_g;   // already rounded to T
+    void* h_par = nullptr;       // pinned host shadow of d_par
+    void* d_par = nullptr;
+    bool dirty = true;
+    void* d_state = nullptr;
+    void* d_xh = nullptr;
+    int xh_cur = 0;
+    hg::DevBuf in_stage, out_stage, bands_stage, partial, scan_a, scan_b;
+    cudaStream_t own_stream = nullptr;
+    int force_F = 0;
+    int force_chunks = 0;
+    // last launch report
+    int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
+};
+
+namespace hg {
+
+template <typename T> struct FbK1Params {
+    const T* par;
+    T* state;
+    const T* xh;
+    T* xh_out;
+    const T* in;
+    T* out;
+    T* bands;
+    long in_stride, out_stride, bands_stride;
+    int N, S;
+    long L;
+    T c_p, s_p, c_g, s_g;
+    int direct;
+    int bands_vec;
+};
+
+template <typename T>
+hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
+template <typename T>
+hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st);
+
+}  // namespace hg

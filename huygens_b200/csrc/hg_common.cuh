@@ -1,0 +1,110 @@
+// hg_common.cuh — shared helpers of libhuygens_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "../../include/huygens_cuda.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libhuygens_cuda is written for sm_100a (B200) only"
+#endif
+
+namespace hg {
+
+// thread-local error text behind hg_last_error()
+char* err_buf();
+hg_status fail(hg_status code, const char* fmt, ...);
+
+#define HG_CUDA(expr)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return hg::fail(HG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,     \
+                            cudaGetErrorString(e__));                                     \
+    } while (0)
+
+#define HG_TRY(expr)                          \
+    do {                                      \
+        hg_status s__ = (expr);               \
+        if (s__ != HG_OK) return s__;         \
+    } while (0)
+
+inline size_t dtype_size(int dtype) { return dtype == HG_F32 ? 4 : 8; }
+
+// true if p is a device (or managed) pointer usable from kernels of the current device
+bool is_device_ptr(const void* p);
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic policies.  STRICT never lets the compiler contract (intrinsics with explicit
+// rounding are never fused by nvcc); FMA uses the one fixed contraction pattern shared with
+// oracle/huygens_oracle.hpp.  `acc` is the order-free accumulation (mixdown), always fused.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> struct Ar;
+
+template <bool FMA> struct Ar<float, FMA> {
+    typedef float T;
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __fsub_rn(a, b); }
+    // fl(a*b + c) fused, or fl(fl(a*b) + c)
+    static __device__ __forceinline__ T muladd(T a, T b, T c) {
+        return FMA ? __fmaf_rn(a, b, c) : __fadd_rn(__fmul_rn(a, b), c);
+    }
+    // fl(a*b - c)
+    static __device__ __forceinline__ T mulsub(T a, T b, T c) {
+        return FMA ? __fmaf_rn(a, b, -c) : __fsub_rn(__fmul_rn(a, b), c);
+    }
+    static __device__ __forceinline__ T acc(T a, T b, T c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ T div(T a, T b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ T sqrt(T a) { return __fsqrt_rn(a); }
+};
+
+template <bool FMA> struct Ar<double, FMA> {
+    typedef double T;
+    static __device__ __forceinline__ T mul(T a, T b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ T add(T a, T b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ T muladd(T a, T b, T c) {
+        return FMA ? __fma_rn(a, b, c) : __dadd_rn(__dmul_rn(a, b), c);
+    }
+    static __device__ __forceinline__ T mulsub(T a, T b, T c) {
+        return FMA ? __fma_rn(a, b, -c) : __dsub_rn(__dmul_rn(a, b), c);
+    }
+    static __device__ __forceinline__ T acc(T a, T b, T c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ T div(T a, T b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ T sqrt(T a) { return __dsqrt_rn(a); }
+};
+
+// Transposed CTA reduction of one tile of per-thread partial sums.
+//   rb[t * RS + tid], RS = NT + NW  (RS == NW mod 32: the per-sample STS of all threads and the
+//   strided reads below are both bank-conflict free).  Warp w owns samples [w*SPW, (w+1)*SPW),
+//   NW lanes per sample, each adding 32 of the NT partials in a fixed order, then a shuffle tree:
+//   deterministic for a given NT.  out[t] is written for t < tn (tile of at most 32 samples).
+template <typename T, int NT>
+__device__ __forceinline__ void cta_tile_reduce(const T* rb, int tn, T* out, int out_step = 1) {
+    constexpr int NW = NT / 32, RS = NT + NW, SPW = 32 / NW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ls = lane / NW, jq = lane % NW;
+    const int t = warp * SPW + ls;
+    const T* row = rb + t * RS + jq;
+    T sum = (T)0;
+    if (t < tn) {
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) sum += row[i * NW];
+    }
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (jq == 0 && t < tn) out[(size_t)t * out_step] = sum;
+}
+
+// staging buffer that grows on demand (device memory)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    hg_status reserve(size_t bytes);
+    void release();
+};
+
+}  // namespace hg

@@ -1,0 +1,125 @@
+/* huygens_cuda.h — C ABI of libhuygens_cuda.so (hand-written sm_100a CUDA).
+ *
+ * The reference (amcerbu/huygens) has no FFI: its boundary is the public surface of the
+ * header-only class templates in namespace soundmath.  Each entry point below names the
+ * reference member it replaces (paths relative to the reference root).  The C++ drop-in
+ * templates in include/huygens/ forward to these; see INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - dtype: HG_F32 / HG_F64.  Every `const void*` / `void*` array is of the handle's dtype.
+ *   - Array pointers given to *_process may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes).  Device pointers: fully asynchronous on `stream`.  Host
+ *     pointers: staged through internal device buffers and synchronised before returning.
+ *   - Setters write a host shadow; it is uploaded at the next *_process call, so parameter
+ *     changes land on block boundaries (the reference's setters race with the audio thread,
+ *     tests/filterbank.cpp:217-252; per-sample smoothing continues on the device).
+ *   - State persists in the handle between calls: rendering L samples in one call is
+ *     bit-identical to any split into consecutive calls (exact mode).
+ *   - Every function returns hg_status; hg_last_error() gives a thread-local message.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device
+ *     hg_*_create fails with HG_ERR_CUDA.
+ */
+#ifndef HUYGENS_CUDA_H
+#define HUYGENS_CUDA_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int hg_status;
+enum { HG_OK = 0, HG_ERR_INVALID = 1, HG_ERR_UNSUPPORTED = 2, HG_ERR_CUDA = 3, HG_ERR_NOMEM = 4 };
+enum { HG_F32 = 0, HG_F64 = 1 };
+/* arithmetic mode: STRICT = every mul/add rounded separately (x86-64 g++ -O3 build of the
+ * reference, tests/build.sh:8); FMA = the fixed contraction pattern of DESIGN.md §3. */
+enum { HG_ARITH_STRICT = 0, HG_ARITH_FMA = 1 };
+/* time strategy: EXACT = serial-in-time lanes, bit-identical per filter to the reference loop;
+ * SCAN = chunked time-parallel scan of the 2x2 state recurrence (not bit-identical; see
+ * DESIGN.md §5 for the measured error); AUTO = EXACT unless few lanes and a long block. */
+enum { HG_MODE_AUTO = 0, HG_MODE_EXACT = 1, HG_MODE_SCAN = 2 };
+/* hg_fb_create flags */
+enum { HG_FB_FIXED = 1 /* FFilterbank<T,N,order> smoothing semantics, src/filterbank.h:203,291 */ };
+/* per-band nonlinearity applied to y_n*g_n before the sum (src/filterbank.h:133-139) */
+enum { HG_DIST_NONE = 0, HG_DIST_SOFTCLIP = 1 /* tests/filterbank.cpp:158-171, width 0.125 */ };
+
+typedef struct hg_fb hg_fb;
+typedef struct hg_osc hg_osc;
+typedef struct hg_rms hg_rms;
+
+const char* hg_last_error(void);
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+int hg_device_count(void);
+/* Measured FP32 (dtype HG_F32) or FP64 FMA issue rate of `device`, in lane-FMA slots per second,
+ * from a register-resident FFMA/DFMA microbenchmark; also returns SM count and the SM clock (MHz)
+ * observed during it.  This is the denominator of the FMA roofline. */
+hg_status hg_fma_peak(int device, int dtype, double* slots_per_s, int* sm_count, double* sm_mhz);
+
+/* ---- Filterbank<T> / FFilterbank<T,N,order>  (src/filterbank.h) -------------------------- */
+/* Filterbank(int order, int N, double k_p, double k_g)  src/filterbank.h:36-70; n_streams
+ * independent banks sharing coefficients and gain targets (tests/filterbanks.cpp:185,195-208),
+ * each with its own input and state.  order <= 2 (every bank in the reference is order 2). */
+hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filters, int n_streams,
+                       double k_p, double k_g, int flags, int device);
+hg_status hg_fb_destroy(hg_fb* fb);
+/* coefficients(n, forward, back)  src/filterbank.h:73-82 for filters n0..n0+count-1.
+ * fwd: [count][n_fwd], back: [count][n_back] (back = a1,a2 with no leading a0).  Only the first
+ * min(order+1, n_fwd) / min(order, n_back) entries are used, the rest keep their value. */
+hg_status hg_fb_set_coefficients(hg_fb* fb, int n0, int count, const void* fwd, int n_fwd,
+                                 const void* back, int n_back);
+/* boost(n, v) / boost(vector)  src/filterbank.h:85-96: targets of the smoothed pre-gain */
+hg_status hg_fb_set_boost(hg_fb* fb, int n0, int count, const void* values);
+/* mix(n, v) / mix(vector)  src/filterbank.h:99-110: targets of the smoothed mixdown gain */
+hg_status hg_fb_set_mix(hg_fb* fb, int n0, int count, const void* values);
+/* open()  src/filterbank.h:112-116 */
+hg_status hg_fb_open(hg_fb* fb);
+/* Block form of the caller loop `out[t] = bank(in[t]); bank.tick();` (operator() :125-131,
+ * compute :170-187, tick :142-148; tests/resynthesis.cpp:33-42).
+ *   in        [n_streams][L]
+ *   out_sum   [n_streams][L]              or NULL
+ *   out_bands [n_streams][n_filters][L]   or NULL  (y_n[t], the private `outputs` row)
+ * distortion != NONE selects operator()(sample, distortion) :133-139. */
+hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_bands, size_t L,
+                        int mode, int distortion, void* cuda_stream);
+/* state access (streaming / checkpoint tests): y1,y2,p,g are [n_streams][n_filters]; xhist is
+ * [n_streams][2] = x[t-1], x[t-2].  Host pointers. NULL entries are skipped. */
+hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void* xhist);
+hg_status hg_fb_set_state(hg_fb* fb, const void* y1, const void* y2, const void* p, const void* g,
+                          const void* xhist);
+/* what the last hg_fb_process did: mode used, kernel launches, filters per thread, CTAs */
+hg_status hg_fb_last_launch(hg_fb* fb, int* mode_used, int* launches, int* filters_per_thread,
+                            int* grid_ctas);
+/* Partial-sum device buffer helper for filter-partitioned multi-GPU runs: the caller reduces
+ * out_sum across ranks (NCCL) — this library never communicates. */
+
+/* ---- Oscbank<T,N>  (src/oscbank.h, src/multichannel.h) ------------------------------------ */
+hg_status hg_osc_create(hg_osc** out, int dtype, int arith, int n_partials, int device);   /* oscbank.h:37-47 */
+hg_status hg_osc_destroy(hg_osc* osc);
+/* freqmod(index, target_hz)  oscbank.h:49-56; out-of-range index is silently ignored (:51) */
+hg_status hg_osc_freqmod(hg_osc* osc, int index, double target_hz);
+hg_status hg_osc_set_frequencies(hg_osc* osc, int n0, int count, const double* target_hz);
+/* Multichannel activate/deactivate/open/close  multichannel.h:87-118 */
+hg_status hg_osc_activate(hg_osc* osc, const int* indices, int count, int on);
+hg_status hg_osc_open(hg_osc* osc);
+hg_status hg_osc_close(hg_osc* osc);
+int hg_osc_active_count(hg_osc* osc);
+/* L ticks.  Per tick t, BEFORE advancing: out_mix[t] = mixdown() (complex interleaved, sum over
+ * the active set, oscbank.h:81-90); out_amix[t] = Mixer(Modbank(amps, osc())) = sum over ALL n of
+ * amps[n]*Re(phase_n) (modbank.h:41-45, mixer.h:32-35); then tick() (oscbank.h:59-63).
+ * Any of out_mix / out_amix may be NULL; amps is [n_partials] and required iff out_amix. */
+hg_status hg_osc_process(hg_osc* osc, void* out_mix, const void* amps, void* out_amix, size_t L,
+                         void* cuda_stream);
+hg_status hg_osc_get_phases(hg_osc* osc, void* phases /* complex interleaved [n_partials], host */);
+hg_status hg_osc_set_phases(hg_osc* osc, const void* phases);
+
+/* ---- RMSbank<T,N>  (src/rmsbank.h) --------------------------------------------------------- */
+hg_status hg_rms_create(hg_rms** out, int dtype, int arith, int n_channels, int width, int device); /* rmsbank.h:32-45 */
+hg_status hg_rms_destroy(hg_rms* rms);
+/* L ticks of `out = rms(z); rms.tick();` (operator() :54-66 evaluated once per tick, tick :68-74).
+ * zre, zim, out: [n_channels][L] channel-major; zim may be NULL (real input). */
+hg_status hg_rms_process(hg_rms* rms, const void* zre, const void* zim, void* out, size_t L,
+                         void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUYGENS_CUDA_H */

@@ -1,0 +1,213 @@
+"""ctypes front-end of the parity oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under huygens_b200/ imports this package.
+
+The classes mirror the reference's public surface (/root/reference/src/filterbank.h:16-188,
+oscbank.h:16-97, rmsbank.h:16-85) plus the caller loop `out[t] = bank(in[t]); bank.tick()`
+(tests/resynthesis.cpp:33-42) as `process`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}
+
+
+def build(verbose=False):
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if os.path.isdir("/root/reference/src") and os.path.exists(os.path.join(_HERE, "ref_capi.cpp")):
+        out = subprocess.run(["make", "-C", _HERE, "ref"], capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError("oracle/_ref build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        for mode in ("strict", "fma"):
+            f = lambda n: getattr(_LIB, f"{n}_{mode}")
+            f("hgo_fb_create").restype = C.c_void_p
+            f("hgo_fb_create").argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+            f("hgo_fb_destroy").argtypes = [C.c_void_p]
+            f("hgo_fb_coefficients").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            f("hgo_fb_boost").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            f("hgo_fb_mix").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            f("hgo_fb_open").argtypes = [C.c_void_p]
+            f("hgo_fb_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+            f("hgo_fb_get_smoothed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            f("hgo_osc_create").restype = C.c_void_p
+            f("hgo_osc_create").argtypes = [C.c_int, C.c_int]
+            f("hgo_osc_destroy").argtypes = [C.c_void_p]
+            f("hgo_osc_freqmod").argtypes = [C.c_void_p, C.c_int, C.c_double]
+            f("hgo_osc_open").argtypes = [C.c_void_p]
+            f("hgo_osc_close").argtypes = [C.c_void_p]
+            f("hgo_osc_activate").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+            f("hgo_osc_active_count").argtypes = [C.c_void_p]
+            f("hgo_osc_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+            f("hgo_osc_get_phases").argtypes = [C.c_void_p, C.c_void_p]
+            f("hgo_rms_create").restype = C.c_void_p
+            f("hgo_rms_create").argtypes = [C.c_int, C.c_int, C.c_int]
+            f("hgo_rms_destroy").argtypes = [C.c_void_p]
+            f("hgo_rms_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Base:
+    def __init__(self, dtype, mode):
+        self.dtype = np.dtype(dtype)
+        assert self.dtype in DTYPES and mode in ("strict", "fma")
+        self.mode = mode
+        self._h = None
+
+    def _f(self, name):
+        return getattr(lib(), f"{name}_{self.mode}")
+
+    def _arr(self, v):
+        return np.ascontiguousarray(np.asarray(v, dtype=np.float64).astype(self.dtype))
+
+
+class Filterbank(_Base):
+    """Filterbank<T>(order, N, k_p, k_g) — filterbank.h:36; fixed=True -> FFilterbank<T,N,order>(k_p,k_g) :203."""
+
+    def __init__(self, order, N=1, k_p=0.1, k_g=1.0, dtype=np.float64, mode="strict", fixed=False):
+        super().__init__(dtype, mode)
+        self.N, self.order = N, order
+        self._h = self._f("hgo_fb_create")(DTYPES[self.dtype], int(fixed), order, N, k_p, k_g)
+
+    def __del__(self):
+        if self._h:
+            self._f("hgo_fb_destroy")(self._h)
+            self._h = None
+
+    def coefficients(self, n, forward, back):
+        f, b = self._arr(forward), self._arr(back)
+        self._f("hgo_fb_coefficients")(self._h, n, _ptr(f), len(f), _ptr(b), len(b))
+
+    def boost(self, a, value=None):
+        if value is None:
+            v = self._arr(a)[: self.N]
+            self._f("hgo_fb_boost")(self._h, 0, len(v), _ptr(v))
+        else:
+            v = self._arr([value])
+            self._f("hgo_fb_boost")(self._h, int(a), 1, _ptr(v))
+
+    def mix(self, a, value=None):
+        if value is None:
+            v = self._arr(a)[: self.N]
+            self._f("hgo_fb_mix")(self._h, 0, len(v), _ptr(v))
+        else:
+            v = self._arr([value])
+            self._f("hgo_fb_mix")(self._h, int(a), 1, _ptr(v))
+
+    def open(self):
+        self._f("hgo_fb_open")(self._h)
+
+    def process(self, x, bands=False, distortion=0, want_sum=True):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        L = len(x)
+        out = np.empty(L, self.dtype) if want_sum else None
+        bd = np.empty((self.N, L), self.dtype) if bands else None
+        self._f("hgo_fb_process")(self._h, _ptr(x), _ptr(out), _ptr(bd), L, distortion)
+        return (out, bd) if bands else out
+
+    def smoothed(self):
+        p = np.empty(self.N, self.dtype)
+        g = np.empty(self.N, self.dtype)
+        self._f("hgo_fb_get_smoothed")(self._h, _ptr(p), _ptr(g))
+        return p, g
+
+
+class Oscbank(_Base):
+    """Oscbank<T,N> — oscbank.h:16-97 (+ Multichannel activate/deactivate/open/close)."""
+
+    def __init__(self, N, dtype=np.float64, mode="strict"):
+        super().__init__(dtype, mode)
+        self.N = N
+        self._h = self._f("hgo_osc_create")(DTYPES[self.dtype], N)
+
+    def __del__(self):
+        if self._h:
+            self._f("hgo_osc_destroy")(self._h)
+            self._h = None
+
+    def freqmod(self, index, target):
+        self._f("hgo_osc_freqmod")(self._h, int(index), float(target))
+
+    def open(self):
+        self._f("hgo_osc_open")(self._h)
+
+    def close(self):
+        self._f("hgo_osc_close")(self._h)
+
+    def activate(self, idx):
+        a = np.ascontiguousarray(idx, dtype=np.int32)
+        self._f("hgo_osc_activate")(self._h, _ptr(a), len(a), 1)
+
+    def deactivate(self, idx):
+        a = np.ascontiguousarray(idx, dtype=np.int32)
+        self._f("hgo_osc_activate")(self._h, _ptr(a), len(a), 0)
+
+    def active_count(self):
+        return self._f("hgo_osc_active_count")(self._h)
+
+    def process(self, L, phases=False, amps=None):
+        """Per tick: mix[t] = mixdown(); [phases[t] = osc()]; [amix[t] = Mixer(Modbank(amps, osc()))]; tick()."""
+        mix = np.empty(L, np.complex64 if self.dtype == np.float32 else np.complex128)
+        ph = np.empty((L, self.N), mix.dtype) if phases else None
+        am = None if amps is None else np.ascontiguousarray(amps, dtype=self.dtype)
+        amix = None if amps is None else np.empty(L, self.dtype)
+        self._f("hgo_osc_process")(self._h, _ptr(mix), _ptr(ph), _ptr(am), _ptr(amix), L)
+        res = [mix]
+        if phases:
+            res.append(ph)
+        if amps is not None:
+            res.append(amix)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def phases(self):
+        p = np.empty(self.N, np.complex64 if self.dtype == np.float32 else np.complex128)
+        self._f("hgo_osc_get_phases")(self._h, _ptr(p))
+        return p
+
+
+class RMSbank(_Base):
+    """RMSbank<T,N>(width = SR/20) — rmsbank.h:16-85."""
+
+    def __init__(self, N, width=2400, dtype=np.float64, mode="strict"):
+        super().__init__(dtype, mode)
+        self.N, self.width = N, width
+        self._h = self._f("hgo_rms_create")(DTYPES[self.dtype], N, width)
+
+    def __del__(self):
+        if self._h:
+            self._f("hgo_rms_destroy")(self._h)
+            self._h = None
+
+    def process(self, zre, zim=None, calls_per_tick=1):
+        """zre/zim: [N][L] channel-major.  Returns out[N][L]."""
+        zre = np.ascontiguousarray(zre, dtype=self.dtype)
+        zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
+        N, L = zre.shape
+        assert N == self.N
+        out = np.empty((N, L), self.dtype)
+        self._f("hgo_rms_process")(self._h, _ptr(zre), _ptr(zim), _ptr(out), L, calls_per_tick)
+        return out

@@ -1,0 +1,305 @@
+// huygens_oracle.hpp — CPU restatement of the huygens filter-ensemble hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity oracle: a dependency-free, literal
+// restatement of the reference's per-sample tick loops.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may compile, link or call it.  The
+// product path (huygens_b200/csrc, include/) never includes it and has no CPU fallback.
+//
+// PARITY STATUS: the arithmetic of the reference lives in Eigen (>= 3.4, un-vendored and
+// unpinned: tests/build.sh:8 only passes -I /opt/homebrew/include/eigen3) and the reference
+// ships no golden vectors, assertions or expected outputs.  The restatement is
+// pinned two ways: (1) closed-form known-answer tests (tests/test_oracle_kat.py); (2)
+// oracle/_ref — the UNMODIFIED reference headers src/{filterbank,oscbank,rmsbank,
+// multichannel}.h compiled where they lie against a minimal Eigen/PortAudio/RtMidi shim
+// (oracle/shim/, ours) — must agree with this file bit-for-bit on seeded inputs
+// (tests/test_oracle_vs_ref.py).  Because the shim is not Eigen itself, Eigen's internal
+// summation orders stay unverified => "parity unpinned" at the last-ulp level of (a) the 3-tap
+// GEMV when b1 != 0 and (b) the N-way mixdown dot.  Every caller in the reference uses
+// b = {b0, 0, -b0}, for which (a) is order-independent.
+//
+// Arithmetic modes (template parameter FMA):
+//   strict (FMA=false): every multiply and add rounded separately.  This is what
+//       `g++ -O3 -std=c++17` (tests/build.sh:8, no -march) produces on x86-64, i.e. what the
+//       reference computes on the GPU box's host.  Compile this TU with -ffp-contract=off.
+//   fma    (FMA=true): one fixed contraction pattern with explicit std::fma (what an arm64 /
+//       -march=native build would plausibly execute).  Compile with -mfma.
+//
+// Reference citations are relative to /root/reference.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace hgoracle {
+
+// src/includes.h:30-32
+static const double PI = 3.14159265359;
+static const int SR = 48000;
+
+// src/includes.h:38-48  relaxation(k) = 2^(log2(eps_double) / (max(0,k) * SR)), k == 0 -> 0
+inline double relaxation(double k) {
+    static const double eps = std::numeric_limits<double>::epsilon();
+    static const double order = std::log2(eps);
+    if (k == 0) return 0;
+    return std::pow(2.0, order / (std::fmax(0, k) * SR));
+}
+
+// tests/resynthesis.cpp:23-27, tests/filterbank.cpp:152-156
+inline std::complex<double> transfer(double frequency, double r, double f) {
+    std::complex<double> z(std::cos(2 * PI * f / SR), -std::sin(2 * PI * f / SR));
+    return (1.0 - z * z) / (1.0 - 2 * r * std::cos(2 * PI * frequency / SR) * z + r * r * z * z);
+}
+
+// tests/filterbank.cpp:158-171
+inline double softclip(double sample, double width) {
+    if (std::abs(sample) < width) return sample;
+    int sign = (0.0 < sample) - (sample < 0.0);
+    double gap = sample - sign * width;
+    return sign * width + (1 - width) * 2.0 / PI * std::atan(PI * gap / (2 * (1 - width)));
+}
+inline double softclip(double sample) { return softclip(sample, 0.125); }
+// src/wave.h:150 (FUNCTIONAL lookup, wave.h:4,65-70)
+inline double limiter(double x) { return 2.0 / PI * std::atan(x); }
+
+template <typename T, bool FMA> struct Arith {
+    static inline T mul(T a, T b) { return a * b; }
+    // a*b + c
+    static inline T muladd(T a, T b, T c) {
+        if (FMA) return std::fma(a, b, c);
+        T m = a * b;
+        return m + c;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Filterbank<T>  (src/filterbank.h:16-188)  and FFilterbank<T,N,order> (src/filterbank.h:191-319)
+// `fixed` selects the FFilterbank flavour, whose smoothing constants are of type T (:291)
+// instead of double (:165).
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class Filterbank {
+public:
+    // src/filterbank.h:36-70 (FF: :203-216)
+    Filterbank(int order, int N, double k_p, double k_g, bool fixed = false)
+        : N(N), order(order) {
+        double sp = relaxation(k_p), sg = relaxation(k_g);
+        if (fixed) {
+            // FFilterbank: `T smoothing_p` (:291); `(1 - smoothing_p)` evaluated in T
+            s_p = (T)sp; s_g = (T)sg;
+            c_p = (T)1 - s_p; c_g = (T)1 - s_g;
+        } else {
+            // Filterbank: `double smoothing_p` (:165); the double scalars (1 - s) and s are
+            // converted to T by Eigen's promote_scalar_arg before the multiply (:172-173)
+            s_p = (T)sp; s_g = (T)sg;
+            c_p = (T)(1 - sp); c_g = (T)(1 - sg);
+        }
+        forwards.assign((size_t)N * (order + 1), 0);
+        backs.assign((size_t)N * std::max(order, 1), 0);
+        input.assign(2 * (order + 1), 0);
+        outputs.assign((size_t)2 * (order + 1) * N, 0);
+        preamps_in.assign(N, 0); preamps_out.assign(N, 0);
+        gains_in.assign(N, 0); gains_out.assign(N, 0);
+    }
+    // :73-82
+    void coefficients(int n, const std::vector<T>& forward, const std::vector<T>& back) {
+        int coeffs = std::min<int>(order + 1, (int)forward.size());
+        for (int i = 0; i < coeffs; i++) forwards[(size_t)n * (order + 1) + i] = forward[i];
+        coeffs = std::min<int>(order, (int)back.size());
+        for (int i = 0; i < coeffs; i++) backs[(size_t)n * order + i] = back[i];
+    }
+    void boost(int n, T value) { preamps_in[n] = value; }                       // :85-88
+    void boost(const std::vector<T>& v) {                                       // :91-96
+        for (int i = 0; i < std::min<int>(N, (int)v.size()); i++) preamps_in[i] = v[i];
+    }
+    void mix(int n, T value) { gains_in[n] = value; }                           // :99-102
+    void mix(const std::vector<T>& v) {                                         // :105-110
+        for (int i = 0; i < std::min<int>(N, (int)v.size()); i++) gains_in[i] = v[i];
+    }
+    void open() { for (int i = 0; i < N; i++) gains_in[i] = 1; }                // :112-116
+
+    // :125-131   outputs.row(origin) * gains_out, summed in index order
+    T operator()(T sample) {
+        if (!computed) compute(sample);
+        T acc = 0;
+        const T* row = &outputs[(size_t)origin * N];
+        for (int n = 0; n < N; n++) acc = Arith<T, FMA>::muladd(row[n], gains_out[n], acc);
+        return acc;
+    }
+    // :133-139   sum_n distortion(y_n * g_n)
+    T operator()(T sample, T (*distortion)(T)) {
+        if (!computed) compute(sample);
+        T acc = 0;
+        const T* row = &outputs[(size_t)origin * N];
+        for (int n = 0; n < N; n++) acc += distortion(row[n] * gains_out[n]);
+        return acc;
+    }
+    // :142-148
+    void tick() {
+        origin--;
+        if (origin < 0) origin += order + 1;
+        computed = false;
+    }
+    // test accessor (the reference keeps `outputs` private, :155): y_n[t] of the current tick
+    const T* bands() const { return &outputs[(size_t)origin * N]; }
+    const T* gains() const { return gains_out.data(); }
+    const T* preamps() const { return preamps_out.data(); }
+    int size() const { return N; }
+
+private:
+    int N, order;
+    T s_p, s_g, c_p, c_g;
+    std::vector<T> forwards, backs;        // N x (order+1), N x order   (row n = filter n)
+    std::vector<T> input;                  // 2(order+1) doubled ring (:51)
+    std::vector<T> outputs;                // 2(order+1) x N doubled ring, row-major by ring slot (:52)
+    std::vector<T> preamps_in, preamps_out, gains_in, gains_out;
+    int origin = 0;
+    bool computed = false;
+
+    // :170-187 (FF :303-318)
+    void compute(T sample) {
+        typedef Arith<T, FMA> A;
+        const int o1 = order + 1;
+        for (int n = 0; n < N; n++) {   // :172-173  p = (1-s)*pin + s*p
+            preamps_out[n] = A::muladd(s_p, preamps_out[n], c_p * preamps_in[n]);
+            gains_out[n] = A::muladd(s_g, gains_out[n], c_g * gains_in[n]);
+        }
+        input[origin] = sample;                                     // :175
+        input[origin + o1] = sample;                                // :176
+        T* y_new = &outputs[(size_t)origin * N];
+        for (int n = 0; n < N; n++) {
+            // :178 GEMV forwards[N x (o+1)] * x[t-i], accumulated over i = 0..order
+            const T* f = &forwards[(size_t)n * o1];
+            T fw = f[0] * input[origin];
+            for (int i = 1; i < o1; i++) fw = A::muladd(f[i], input[origin + i], fw);
+            // :179 (backs * outputs.block(origin+1, 0, order, N)).diagonal()
+            T fb = 0;
+            if (order > 0) {
+                const T* b = &backs[(size_t)n * order];
+                fb = b[0] * outputs[(size_t)(origin + 1) * N + n];
+                for (int i = 1; i < order; i++)
+                    fb = A::muladd(b[i], outputs[(size_t)(origin + 1 + i) * N + n], fb);
+            }
+            // :178-179  temp = fw .* preamps_out - fb
+            T y;
+            if (FMA) y = std::fma(fw, preamps_out[n], -fb);
+            else { T u = fw * preamps_out[n]; y = u - fb; }
+            y_new[n] = y;
+        }
+        std::memcpy(&outputs[(size_t)(origin + o1) * N], y_new, sizeof(T) * N);   // :183-184
+        computed = true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Multichannel<T,N>  (src/multichannel.h:16-159): sorted active-index list + bool mask.
+// The recursive binary-search insert/erase (:121-157) is a sorted-set insert/erase; restated
+// as such.  All channels start inactive (:19-24).
+// ---------------------------------------------------------------------------------------------
+class Multichannel {
+public:
+    explicit Multichannel(int N) : N(N), active(N, 0) {}
+    void activate(const std::vector<int>& idx) {                               // :87-92
+        for (int i : idx)
+            if (0 <= i && i < N && !active[i]) {
+                where.insert(std::lower_bound(where.begin(), where.end(), i), i);
+                active[i] = 1;
+            }
+    }
+    void deactivate(const std::vector<int>& idx) {                             // :95-100
+        for (int i : idx)
+            if (0 <= i && i < N && active[i]) {
+                where.erase(std::lower_bound(where.begin(), where.end(), i));
+                active[i] = 0;
+            }
+    }
+    void open() { std::vector<int> v(N); for (int i = 0; i < N; i++) v[i] = i; activate(v); }    // :103-109
+    void close() { std::vector<int> v(N); for (int i = 0; i < N; i++) v[i] = i; deactivate(v); } // :112-118
+    int N;
+    std::vector<char> active;
+    std::vector<int> where;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Oscbank<T,N>  (src/oscbank.h:16-97)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class Oscbank : public Multichannel {
+public:
+    explicit Oscbank(int N) : Multichannel(N), re(N, 1), im(N, 0), fr(N, 1), fi(N, 0) {}   // :37-47
+    // :49-56
+    void freqmod(int index, T target) {
+        if (0 <= index && index < N) {
+            fr[index] = (T)std::cos(2 * PI * target / SR);
+            fi[index] = (T)std::sin(2 * PI * target / SR);
+        }
+    }
+    // :59-63   p *= f ;  p /= (1 + |p|^2) / 2     over the active set
+    void tick() {
+        for (int i : where) {
+            T a = re[i], b = im[i], c = fr[i], d = fi[i];
+            T nr, ni, q;
+            if (FMA) {
+                nr = std::fma(-b, d, a * c);
+                ni = std::fma(b, c, a * d);
+                q = std::fma(ni, ni, nr * nr);
+            } else {
+                T ac = a * c, bd = b * d, ad = a * d, bc = b * c;
+                nr = ac - bd;
+                ni = ad + bc;
+                T r2 = nr * nr, i2 = ni * ni;
+                q = r2 + i2;
+            }
+            T m = ((T)1 + q) / (T)2;
+            re[i] = nr / m;
+            im[i] = ni / m;
+        }
+    }
+    // :81-90
+    std::complex<T> mixdown() const {
+        T sr = 0, si = 0;
+        for (int i : where) { sr += re[i]; si += im[i]; }
+        return std::complex<T>(sr, si);
+    }
+    std::vector<T> re, im, fr, fi;
+};
+
+// ---------------------------------------------------------------------------------------------
+// RMSbank<T,N>  (src/rmsbank.h:16-85)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class RMSbank : public Multichannel {
+public:
+    RMSbank(int N, int width) : Multichannel(N), width(width), origin(0),
+        inputs((size_t)N * 2 * (width + 1), 0), out(N, 0), lastout(N, 0) {}     // :32-45
+    // :54-66   input: N complex samples (re[], im[]).  Returns out (in place sqrt, every call)
+    const T* operator()(const T* zre, const T* zim) {
+        const size_t W2 = 2 * (size_t)(width + 1);
+        if (!computed) {
+            for (int n = 0; n < N; n++) {
+                T q;
+                if (FMA) q = std::fma(zim[n], zim[n], zre[n] * zre[n]);
+                else { T a = zre[n] * zre[n], b = zim[n] * zim[n]; q = a + b; }
+                T* ring = &inputs[(size_t)n * W2];
+                ring[origin] = q;                                                // :58
+                ring[origin + (width + 1)] = q;                                  // :59
+                T d = ring[origin] - ring[origin + width];                       // :60
+                out[n] = d + lastout[n];
+                lastout[n] = out[n];                                             // :61
+            }
+            computed = true;
+        }
+        for (int n = 0; n < N; n++) out[n] = std::sqrt(out[n] / (T)width);       // :64
+        return out.data();
+    }
+    // :68-74
+    void tick() {
+        origin--;
+        if (origin < 0) origin += width + 1;
+        computed = false;
+    }
+    int width, origin;
+    bool computed = false;
+    std::vector<T> inputs, out, lastout;
+};
+
+}  // namespace hgoracle

@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/huygens_cuda.h declares, and fails loudly (no fallback) without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import huygens_b200 as hb
+from huygens_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    hb.build()
+    return hb.lib()
+
+
+def test_header_symbols_are_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "huygens_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in huygens_cuda.h but not exported"
+    assert declared == {s[0] for s in _lib.SYMBOLS}, "python binding table out of sync with the header"
+
+
+def test_no_cpu_fallback(built):
+    if built.hg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(hb.HuygensError) as e:
+        hb.Filterbank(2, 8, dtype=np.float32)
+    assert e.value.status == _lib.HG_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(hb.HuygensError):
+        hb.Oscbank(8)
+    with pytest.raises(hb.HuygensError):
+        hb.RMSbank(8)
+
+
+def test_product_does_not_use_oracle():
+    """The oracle is test infrastructure: nothing under huygens_b200/ or include/ may import,
+    include or link it."""
+    bad = re.compile(r"import\s+oracle|from\s+oracle|#include\s+\"[^\"]*oracle|liboracle|-loracle")
+    for top in ("huygens_b200", "include", "harness"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not bad.search(text), os.path.join(dirpath, f)
