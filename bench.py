@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — filter-samples/s of the biquad-bank hot path on B200 (BASELINE.json metric).
+
+A step is one pass of the hot path over one block of synthetic input: a Filterbank<float> of 4096
+log-spaced resonant biquads (tests/filterbank.cpp:255-271 recipe) rendering 60 s of a 48 kHz
+chirp to its bank sum (BASELINE.json configs[1]).  With N > 1 GPUs the bank is filter-partitioned
+(each rank owns 4096 more filters: weak scaling) and the partial sums are reduced to rank 0 with
+one NCCL reduce per block — the path's only exchange step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode exact|scan]
+
+`value`   device-resident throughput (CUDA events on the launching stream, L2 flushed between steps)
+`e2e`     same metric through the public API with HOST buffers (pinned), H2D + D2H inside the timing
+`roofline` FP32 FMA-pipe roofline: algorithmic 11 issue slots per filter-sample over
+          the FFMA rate measured live by hg_fma_peak
+`cpu_baseline` the oracle's strict tick loop on one host core over a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000
+SLOTS_PER_FILTER_SAMPLE = 11        # 11 mul + 7 add, every add fusable: SURVEY.md §8(d)
+WORKLOADS = {
+    # name: (filters per GPU, seconds, f_lo, f_hi, r, k_p, k_g, input)
+    "c2": dict(N=4096, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="exact", choices=["exact", "scan", "auto"])
+    ap.add_argument("--arith", default="strict", choices=["strict", "fma"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--seconds", type=float, default=None, help="override block length (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def bank_params(w, rank, world):
+    from huygens_b200 import design
+    N = w["N"]
+    freqs = design.log_spaced(N * world, w["f_lo"], w["f_hi"])[rank * N:(rank + 1) * N]
+    return design.resonator_bank(freqs, w["r"])
+
+
+def make_bank(cls, w, rank, world, dtype, **kw):
+    fwd, back, gains = bank_params(w, rank, world)
+    fb = cls(2, w["N"], w["k_p"], w["k_g"], dtype=dtype, **kw)
+    fb.coefficients(0, fwd, back)
+    fb.mix(gains)
+    fb.boost(np.ones(w["N"]))
+    return fb
+
+
+def synth_input(w, L, dtype):
+    from huygens_b200 import design
+    if w["input"] == "chirp":
+        return design.chirp(L, dtype=dtype)
+    return design.white_noise(L, dtype=dtype)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if mx and c > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(w, dtype, n_samples, threads):
+    """Oracle strict tick loop over the head of the same input; `threads` bank partitions in parallel
+    (the reference itself is single-threaded; partitioning filters is what a host could do)."""
+    import oracle
+    oracle.build()
+    N = w["N"]
+    x = synth_input(w, int(w["seconds"] * SR), dtype)[:n_samples]
+    fwd, back, gains = bank_params(w, 0, 1)
+    parts = np.array_split(np.arange(N), threads)
+    banks = []
+    for idx in parts:
+        fb = oracle.Filterbank(2, len(idx), w["k_p"], w["k_g"], dtype=dtype, mode="strict")
+        for j, n in enumerate(idx):
+            fb.coefficients(j, fwd[n], back[n])
+        fb.mix(gains[idx])
+        fb.boost(np.ones(len(idx)))
+        banks.append(fb)
+    outs = [None] * threads
+
+    def run(i):
+        outs[i] = banks[i].process(x)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        run(0)
+    else:
+        th = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return N * n_samples / dt, dt
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's CPU tick loop (oracle restatement; the reference itself
+    cannot be compiled here — Eigen/PortAudio/RtMidi absent) on all host cores."""
+    if rank != 0:
+        return
+    dtype = np.float32
+    threads = os.cpu_count() or 1
+    n_samples = 2 * SR                       # bounded sample per step: 2 s of the 60 s block
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(w, dtype, n_samples // 4, threads)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_baseline(w, dtype, n_samples, threads)
+        times.append(dt)
+    T = float(np.mean(times))
+    val = w["N"] * n_samples / T
+    sample = f"{w['N']} filters x first {n_samples} samples of the 60 s chirp per step, {threads} threads over filter partitions"
+    line = {
+        "impl": "reference", "metric": "filter-samples/s (biquad bank)", "value": val, "unit": "filter-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, args, world),
+        "cpu_baseline": {"value": val, "unit": "filter-samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "filter-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, world):
+    return {"workload": f"Filterbank<float> {w['N']} log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, "
+                        f"fwd {{1,0,-1}}, k_p={w['k_p']}, k_g={w['k_g']}), {w['seconds']} s 48 kHz {w['input']}, summed output",
+            "filters_per_gpu": w["N"], "filters_total": w["N"] * world, "samples": int(w["seconds"] * SR),
+            "partition": "filters" if world > 1 else "none", "mode": args.mode, "arith": args.arith,
+            "l2": "flushed between steps (256 MiB write)"}
+
+
+def main():
+    args = parse()
+    w = dict(WORKLOADS[args.workload])
+    if args.seconds:
+        w["seconds"] = args.seconds
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import huygens_b200 as hb
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype, tdtype = np.float32, torch.float32
+    L = int(w["seconds"] * SR)
+    N = w["N"]
+    fb = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local)
+    x_host = torch.from_numpy(synth_input(w, L, dtype)).pin_memory()
+    out_host = torch.empty(L, dtype=tdtype).pin_memory()
+    x = x_host.cuda(non_blocking=True)
+    out = torch.empty(L, dtype=tdtype, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peak = hb.fma_peak(np.float32, device=local)
+
+    def step():
+        fb.process(x, out=out, mode=args.mode)
+        if world > 1:
+            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = fb.last_launch()["launches"]
+    info = fb.last_launch()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                    # L2 flush, outside the timed events
+        ev[i][0].record()
+        kev[i][0].record()
+        fb.process(x, out=out, mode=args.mode)
+        kev[i][1].record()
+        if world > 1:
+            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_total, t_kernel], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_total, t_kernel = tt.tolist()
+
+    # end to end through the public API with host buffers (H2D + D2H inside the call)
+    xh, oh = x_host.numpy(), out_host.numpy()
+    for _ in range(2):
+        fb.process(xh, out=oh, mode=args.mode)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fb.process(xh, out=oh, mode=args.mode)       # synchronises before returning
+        if world > 1:
+            # partial sums meet on rank 0: host -> device -> reduce would double count copies; the
+            # device-side reduce of the staged output is what a sharded caller does
+            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = tt.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    units = float(N) * world * L * args.steps
+    value = units / t_total
+    per_gpu_kernel = float(N) * L * args.steps / t_kernel
+    achieved = per_gpu_kernel * SLOTS_PER_FILTER_SAMPLE
+    nominal = peak["sm_count"] * 128 * 1.965e9
+    line = {
+        "metric": "filter-samples/s (biquad bank)", "value": value, "unit": "filter-samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, args, world),
+        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(L * 4), "d2h_bytes_per_step": int(L * 4)},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
+                     "frac": achieved / peak["slots_per_s"], "traffic": None,
+                     "peak_source": "hg_fma_peak FFMA microbenchmark, measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                     "frac_of_nominal": achieved / nominal, "slots_per_unit": SLOTS_PER_FILTER_SAMPLE,
+                     "kernel_ms": t_kernel / args.steps * 1e3, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
+                     "ctas": info["ctas"]},
+    }
+    if not args.no_cpu_baseline:
+        n_s = 3 * SR
+        v, dt = cpu_baseline(w, dtype, n_s, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "filter-samples/s", "cores": 1, "kind": "port",
+                                "sample": f"{N} filters x first {n_s} samples of the same chirp, strict oracle, {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T* sink, int iters, T a, T b, long long* clk) {
     T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
     long long c0 = clock64();
+    unsigned long long g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
@@ -61,9 +63,11 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* sink, int iters, T a, 
         }
     }
     long long c1 = clock64();
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
     T r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
     if (r == (T)123456789) sink[0] = r;   // never true; keeps the chains alive
-    if (blockIdx.x == 0 && threadIdx.x == 0) clk[0] = c1 - c0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = c1 - c0; clk[1] = (long long)(g1 - g0); }
 }
 
 template <typename T>
@@ -74,7 +78,7 @@ static hg_status fma_peak_T(int device, double* slots, int* sms, double* mhz) {
     T* sink;
     long long* clk;
     HG_CUDA(cudaMalloc(&sink, sizeof(T)));
-    HG_CUDA(cudaMalloc(&clk, sizeof(long long)));
+    HG_CUDA(cudaMalloc(&clk, 2 * sizeof(long long)));
     const int ctas = prop.multiProcessorCount * 8, nt = 256;
     const int iters = sizeof(T) == 4 ? 4096 : 2048;
     cudaEvent_t e0, e1;
@@ -89,14 +93,12 @@ static hg_status fma_peak_T(int device, double* slots, int* sms, double* mhz) {
         float ms = 0;
         HG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         double s = (double)ctas * nt * 64.0 * iters / (ms * 1e-3);
-        long long cyc = 0;
-        HG_CUDA(cudaMemcpy(&cyc, clk, sizeof(cyc), cudaMemcpyDeviceToHost));
+        long long cyc[2] = {0, 0};
+        HG_CUDA(cudaMemcpy(cyc, clk, sizeof(cyc), cudaMemcpyDeviceToHost));
         if (rep >= 1 && s > best) {
             best = s;
-            // block 0 runs 1/8 .. of the kernel; its cycle count over its own span gives the clock
-            // indirectly: slots per SM per cycle is 128 (fp32) only if issue-perfect, so report the
-            // clock from total time instead: cycles(block0) / (time share of one wave)
-            best_mhz = (double)cyc / (ms * 1e-3) / 1e6;
+            // SM clock seen by block 0: its cycle counter against the nanosecond global timer
+            best_mhz = cyc[1] > 0 ? (double)cyc[0] / (double)cyc[1] * 1e3 : 0;
         }
     }
     *slots = best;

@@ -269,6 +269,12 @@ static void k1_config(const hg_fb* fb, int* F_out, int* groups_out) {
     const long lanes = (long)fb->N * fb->S;
     const long smsp_threads = (long)fb->sm_count * 4 * 32;   // one warp per scheduler
     int F = 1;
+    // latency-bound regime (at most ~2 CTAs of 32 filters per SM): the warp-specialised kernel, F = 0
+    if (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 64)) {
+        *F_out = 0;
+        *groups_out = (fb->N + 31) / 32;
+        return;
+    }
     if (fb->force_F > 0) F = fb->force_F;
     else if (lanes >= smsp_threads * 8 * 2) F = 8;
     else if (lanes >= smsp_threads * 4) F = 4;
@@ -318,7 +324,8 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
-        if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
+        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, P, groups, st);
+        else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);
         fb->last_launches++;

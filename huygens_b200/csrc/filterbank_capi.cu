@@ -76,8 +76,7 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     if ((ce = cudaMallocHost(&fb->h_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_state, 4 * S * N * es)) != cudaSuccess ||
-        (ce = cudaMalloc(&fb->d_xh, 2 * S * 2 * es)) != cudaSuccess ||
-        (ce = cudaStreamCreateWithFlags(&fb->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (ce = cudaMalloc(&fb->d_xh, 2 * S * 2 * es)) != cudaSuccess ) {
         hg_fb_destroy(fb);
         return hg::fail(HG_ERR_NOMEM, "hg_fb_create: allocation failed: %s", cudaGetErrorString(ce));
     }
@@ -92,7 +91,7 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
 hg_status hg_fb_destroy(hg_fb* fb) {
     if (!fb) return HG_OK;
     cudaSetDevice(fb->device);
-    if (fb->own_stream) { cudaStreamSynchronize(fb->own_stream); cudaStreamDestroy(fb->own_stream); }
+    cudaDeviceSynchronize();
     if (fb->h_par) cudaFreeHost(fb->h_par);
     if (fb->d_par) cudaFree(fb->d_par);
     if (fb->d_state) cudaFree(fb->d_state);
@@ -158,7 +157,7 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
     if (!out_sum && !out_bands) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
     HG_CUDA(cudaSetDevice(fb->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : fb->own_stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;   // NULL = the legacy default stream, as in the CUDA runtime
     const size_t es = hg::dtype_size(fb->dtype);
     const size_t S = fb->S, N = fb->N;
 

@@ -1,0 +1,315 @@
+// filterbank_ws.cu — K1-ws: warp-specialised exact Filterbank kernel for the latency-bound regime
+// (few lanes, long blocks: BASELINE configs[1], 4096 filters x 2.88 M samples).
+//
+// Per filter and sample the reference (src/filterbank.h:170-187) computes
+//     u = fl(fl(fl(b0 x0 + b1 x1) + b2 x2) * p)          feed-forward: independent of y
+//     y = fl(u - fl(fl(a1 y1) + fl(a2 y2)))              recurrence: FMUL -> FADD -> FADD chain
+//     v = fl(y * g)                                       mixdown term
+// Bit-exact replay means the y chain costs 3 dependent FP32 ops = 12 cycles per sample and cannot
+// be shortened; everything else can move off the critical warp.  One CTA = 32 filters of one
+// stream, four warps, one per SM sub-partition:
+//     L (loader)     TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of the input into a
+//                    3-deep ring of 1024-sample chunks; falls back to plain loads when unaligned
+//     U (forward)    lane = filter: u tiles [32][TILE] into shared memory, owns the p smoother
+//     R (recurrence) lane = filter: LDS.128 u -> 4 chained samples -> STS.128 v, owns y1,y2 and g
+//     S (sum)        lane = sample: out[t] = sum over the 32 lanes of v, fixed order; also streams
+//                    per-band rows in bands mode
+// Tiles are handed over with full/empty mbarriers; no __syncthreads in the steady state.
+#include <type_traits>
+#include "hg_common.cuh"
+#include "filterbank_handle.cuh"
+
+namespace hg {
+
+namespace ws {
+
+constexpr int XT = 1024;      // input chunk (samples)
+constexpr int XB = 3;         // input ring depth
+constexpr int NB = 3;         // u / v tile ring depth
+
+template <typename T> struct Cfg;
+template <> struct Cfg<float> { static constexpr int TILE = 128, RS = 132; };    // RS/4 odd: conflict-free 128-bit rows
+template <> struct Cfg<double> { static constexpr int TILE = 64, RS = 66; };      // RS/2 odd
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    while (!mbar_test(b, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&x)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&x)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<double>(const double* p, double (&x)[4]) {
+    double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const T (&x)[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float (&x)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+template <> __device__ __forceinline__ void st4<double>(double* p, const double (&x)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(x[0], x[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(x[2], x[3]);
+}
+
+template <typename T> struct Smem {
+    static constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
+    alignas(16) T xs[XB][XT];
+    alignas(16) T u[NB][32 * RS];
+    alignas(16) T v[NB][32 * RS];
+    unsigned long long x_full[XB], x_empty[XB], u_full[NB], u_empty[NB], v_full[NB], v_empty[NB];
+};
+template <typename T> struct SmemBands : Smem<T> {
+    alignas(16) T y[NB][32 * Cfg<T>::RS];
+};
+
+}  // namespace ws
+
+template <typename T, bool FMA, bool BANDS>
+__global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
+    using namespace ws;
+    typedef Ar<T, FMA> A;
+    constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
+    typedef typename std::conditional<BANDS, SmemBands<T>, Smem<T>>::type SM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+
+    const int lane = threadIdx.x & 31;
+    const int grp = blockIdx.x, s = blockIdx.y;
+    // rotate roles with the CTA index so that co-resident CTAs put their R warps on different schedulers
+    const int role = ((threadIdx.x >> 5) + grp) & 3;     // 0 = R, 1 = U, 2 = S, 3 = L
+    const int N = P.N;
+    const long L = P.L;
+    const int n = grp * 32 + lane;
+    const bool ok = n < N;
+    const size_t SN = (size_t)P.S * N, si = (size_t)s * N + n;
+    const long ntiles = (L + TILE - 1) / TILE;
+    const long nchunks = (L + XT - 1) / XT;
+    constexpr int TPC = XT / TILE;       // tiles per input chunk
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XB; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_empty[i], 1); }
+        for (int i = 0; i < NB; i++) {
+            mbar_init(&sm.u_full[i], 1); mbar_init(&sm.u_empty[i], 1);
+            mbar_init(&sm.v_full[i], 1); mbar_init(&sm.v_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (role == 3) {
+        // ---------------- L: input loader ----------------
+        const T* inp = P.in + (size_t)s * P.in_stride;
+        for (long c = 0; c < nchunks; c++) {
+            const int b = (int)(c % XB);
+            mbar_wait(&sm.x_empty[b], (unsigned)(((c / XB) & 1) ^ 1));
+            const long base = c * XT;
+            const int cnt = (int)min((long)XT, L - base);
+            const T* src = inp + base;
+            const unsigned bytes = (unsigned)(cnt * sizeof(T));
+            if ((((uintptr_t)src) & 15) == 0 && (bytes & 15) == 0) {
+                if (lane == 0) {
+                    mbar_arrive_tx(&sm.x_full[b], bytes);
+                    bulk_g2s(sm.xs[b], src, bytes, &sm.x_full[b]);
+                }
+            } else {
+                for (int i = lane; i < cnt; i += 32) sm.xs[b][i] = src[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.x_full[b]);
+            }
+        }
+    } else if (role == 1) {
+        // ---------------- U: feed-forward taps and pre-gain ----------------
+        const T b0 = ok ? P.par[0 * (size_t)N + n] : (T)0, b1 = ok ? P.par[1 * (size_t)N + n] : (T)0;
+        const T b2 = ok ? P.par[2 * (size_t)N + n] : (T)0;
+        const T pin = ok ? P.par[5 * (size_t)N + n] : (T)0;
+        T p = ok ? P.state[2 * SN + si] : (T)0;
+        const T cp = A::mul(P.c_p, pin), s_p = P.s_p;
+        T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
+        // strict: U owns the p smoother (u = fl(fw*p)); fma: y = fma(fw, p, -fb) needs p in R instead
+        bool conv = FMA ? true : __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+        for (long k = 0; k < ntiles; k++) {
+            const long c = k / TPC;
+            const int xb = (int)(c % XB), ub = (int)(k % NB);
+            if (k % TPC == 0) mbar_wait(&sm.x_full[xb], (unsigned)((c / XB) & 1));
+            mbar_wait(&sm.u_empty[ub], (unsigned)(((k / NB) & 1) ^ 1));
+            const T* xc = sm.xs[xb] + (k % TPC) * TILE;
+            T* urow = sm.u[ub] + lane * RS;
+            const int tn = (int)min((long)TILE, L - k * TILE);
+            int tt = 0;
+            if (conv) {
+#pragma unroll 4
+                for (; tt + 4 <= tn; tt += 4) {
+                    T xv[4], uv[4];
+                    ld4<T>(xc + tt, xv);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        T fw = A::mul(b0, xv[j]);                       // filterbank.h:178
+                        fw = A::muladd(b1, x1, fw);
+                        fw = A::muladd(b2, x2, fw);
+                        uv[j] = FMA ? fw : A::mul(fw, p);               // strict: u = fl(fw*p); fma: fused in R
+                        x2 = x1; x1 = xv[j];
+                    }
+                    st4<T>(urow + tt, uv);
+                }
+            }
+            for (; tt < tn; tt++) {
+                if (!conv) p = A::muladd(s_p, p, cp);                   // filterbank.h:172
+                const T x0 = xc[tt];
+                T fw = A::mul(b0, x0);
+                fw = A::muladd(b1, x1, fw);
+                fw = A::muladd(b2, x2, fw);
+                urow[tt] = FMA ? fw : A::mul(fw, p);
+                x2 = x1; x1 = x0;
+            }
+            if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&sm.u_full[ub]);
+                if (k % TPC == TPC - 1 || k == ntiles - 1) mbar_arrive(&sm.x_empty[xb]);
+            }
+        }
+        if (ok && !FMA) P.state[2 * SN + si] = p;
+        if (grp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+    } else if (role == 0) {
+        // ---------------- R: the recurrence ----------------
+        const T a1 = ok ? P.par[3 * (size_t)N + n] : (T)0, a2 = ok ? P.par[4 * (size_t)N + n] : (T)0;
+        const T gin = ok ? P.par[6 * (size_t)N + n] : (T)0;
+        T y1 = ok ? P.state[0 * SN + si] : (T)0, y2 = ok ? P.state[1 * SN + si] : (T)0;
+        T g = ok ? P.state[3 * SN + si] : (T)0;
+        T p = ok ? P.state[2 * SN + si] : (T)0;           // fma mode only
+        const T pin = ok ? P.par[5 * (size_t)N + n] : (T)0;
+        const T cg = A::mul(P.c_g, gin), s_g = P.s_g, cp = A::mul(P.c_p, pin), s_p = P.s_p;
+        bool gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
+        bool pconv = FMA ? __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p) : true;
+        for (long k = 0; k < ntiles; k++) {
+            const int ub = (int)(k % NB);
+            mbar_wait(&sm.u_full[ub], (unsigned)((k / NB) & 1));
+            mbar_wait(&sm.v_empty[ub], (unsigned)(((k / NB) & 1) ^ 1));
+            const T* urow = sm.u[ub] + lane * RS;
+            T* vrow = sm.v[ub] + lane * RS;
+            T* yrow = BANDS ? (reinterpret_cast<SmemBands<T>&>(sm).y[ub] + lane * RS) : nullptr;
+            const int tn = (int)min((long)TILE, L - k * TILE);
+            int tt = 0;
+            if (gconv && pconv) {
+                T un[4];
+                if (tn >= 4) ld4<T>(urow, un);
+#pragma unroll 4
+                for (; tt + 4 <= tn; tt += 4) {
+                    T uc[4] = {un[0], un[1], un[2], un[3]};
+                    if (tt + 8 <= tn) ld4<T>(urow + tt + 4, un);       // prefetch the next group
+                    T vv[4], yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        T fb = A::mul(a1, y1);                          // filterbank.h:179
+                        fb = A::muladd(a2, y2, fb);
+                        const T y = FMA ? A::mulsub(uc[j], p, fb) : A::sub(uc[j], fb);     // :178-179
+                        y2 = y1; y1 = y;
+                        yy[j] = y;
+                        vv[j] = A::mul(y, g);                           // :130 product; the sum is S's job
+                    }
+                    st4<T>(vrow + tt, vv);
+                    if (BANDS) st4<T>(yrow + tt, yy);
+                }
+            }
+            for (; tt < tn; tt++) {
+                if (!gconv) g = A::muladd(s_g, g, cg);                  // filterbank.h:173
+                if (FMA && !pconv) p = A::muladd(s_p, p, cp);           // filterbank.h:172 (fma mode: p lives here)
+                T fb = A::mul(a1, y1);
+                fb = A::muladd(a2, y2, fb);
+                const T y = FMA ? A::mulsub(urow[tt], p, fb) : A::sub(urow[tt], fb);
+                y2 = y1; y1 = y;
+                vrow[tt] = A::mul(y, g);
+                if (BANDS) yrow[tt] = y;
+            }
+            if (!gconv) gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
+            if (FMA && !pconv) pconv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&sm.u_empty[ub]); mbar_arrive(&sm.v_full[ub]); }
+        }
+        if (ok) {
+            P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[3 * SN + si] = g;
+            if (FMA) P.state[2 * SN + si] = p;
+        }
+    } else {
+        // ---------------- S: mixdown over the 32 lanes, per-band rows ----------------
+        T* out_row = nullptr;
+        if (P.out) out_row = P.direct ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
+        const int rows = min(32, N - grp * 32);
+        for (long k = 0; k < ntiles; k++) {
+            const int ub = (int)(k % NB);
+            mbar_wait(&sm.v_full[ub], (unsigned)((k / NB) & 1));
+            const T* vt = sm.v[ub];
+            const int tn = (int)min((long)TILE, L - k * TILE);
+            const long tg = k * TILE;
+            if (out_row) {
+#pragma unroll
+                for (int j = 0; j < TILE / 32; j++) {
+                    const int t = lane + 32 * j;
+                    T sum = (T)0;
+#pragma unroll 8
+                    for (int l = 0; l < 32; l++) sum += vt[l * RS + t];   // fixed order: deterministic
+                    if (t < tn) out_row[tg + t] = sum;
+                }
+            }
+            if (BANDS) {
+                const T* yt = reinterpret_cast<SmemBands<T>&>(sm).y[ub];
+                for (int r = 0; r < rows; r++) {
+                    T* dst = P.bands + ((size_t)s * N + grp * 32 + r) * P.bands_stride + tg;
+#pragma unroll
+                    for (int j = 0; j < TILE / 32; j++) {
+                        const int t = lane + 32 * j;
+                        if (t < tn) dst[t] = yt[r * RS + t];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.v_empty[ub]);
+        }
+    }
+}
+
+template <typename T, bool FMA, bool BANDS>
+static hg_status launch_ws(const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    typedef typename std::conditional<BANDS, ws::SmemBands<T>, ws::Smem<T>>::type SM;
+    const size_t smem = sizeof(SM);
+    auto kern = fb_exact_ws_kernel<T, FMA, BANDS>;
+    HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(groups, P.S), 128, smem, st>>>(P);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}
+
+template <typename T>
+hg_status fb_launch_exact_ws(bool fma, bool bands, const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    if (bands) return fma ? launch_ws<T, true, true>(P, groups, st) : launch_ws<T, false, true>(P, groups, st);
+    return fma ? launch_ws<T, true, false>(P, groups, st) : launch_ws<T, false, false>(P, groups, st);
+}
+template hg_status fb_launch_exact_ws<float>(bool, bool, const FbK1Params<float>&, int, cudaStream_t);
+template hg_status fb_launch_exact_ws<double>(bool, bool, const FbK1Params<double>&, int, cudaStream_t);
+
+}  // namespace hg

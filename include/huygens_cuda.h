@@ -8,7 +8,8 @@
  * Conventions
  *   - dtype: HG_F32 / HG_F64.  Every `const void*` / `void*` array is of the handle's dtype.
  *   - Array pointers given to *_process may be HOST or DEVICE pointers (detected with
- *     cudaPointerGetAttributes).  Device pointers: fully asynchronous on `stream`.  Host
+ *     cudaPointerGetAttributes).  Device pointers: fully asynchronous on `cuda_stream`
+ *     (a cudaStream_t; NULL = the legacy default stream).  Host
  *     pointers: staged through internal device buffers and synchronised before returning.
  *   - Setters write a host shadow; it is uploaded at the next *_process call, so parameter
  *     changes land on block boundaries (the reference's setters race with the audio thread,
