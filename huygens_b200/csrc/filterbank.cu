@@ -269,8 +269,9 @@ static void k1_config(const hg_fb* fb, int* F_out, int* groups_out) {
     const long lanes = (long)fb->N * fb->S;
     const long smsp_threads = (long)fb->sm_count * 4 * 32;   // one warp per scheduler
     int F = 1;
-    // latency-bound regime (at most ~2 CTAs of 32 filters per SM): the warp-specialised kernel, F = 0
-    if (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 64)) {
+    // latency-bound regime (every CTA of 32 filters resident at once, one per SM): the
+    // warp-specialised kernel, reported as F = 0
+    if (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 32)) {
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
         return;

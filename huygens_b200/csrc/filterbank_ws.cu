@@ -11,8 +11,8 @@
 //     L (loader)     TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of the input into a
 //                    3-deep ring of 1024-sample chunks; falls back to plain loads when unaligned
 //     U (forward)    lane = filter: u tiles [32][TILE] into shared memory, owns the p smoother
-//     R (recurrence) lane = filter: LDS.128 u -> 4 chained samples -> STS.128 v, owns y1,y2 and g
-//     S (sum)        lane = sample: out[t] = sum over the 32 lanes of v, fixed order; also streams
+//     R (recurrence) lane = filter: LDS.128 u -> chained samples -> STS.128 y, owns y1,y2 and g
+//     S (sum)        lane = sample: out[t] = sum over the 32 lanes of y*g, fixed order; also streams
 //                    per-band rows in bands mode
 // Tiles are handed over with full/empty mbarriers; no __syncthreads in the steady state.
 #include <type_traits>
@@ -79,12 +79,12 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
 template <typename T> struct Smem {
     static constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
     alignas(16) T xs[XB][XT];
-    alignas(16) T u[NB][32 * RS];
-    alignas(16) T v[NB][32 * RS];
+    alignas(16) T u[NB][32 * RS];      // U -> R: feed-forward terms
+    alignas(16) T y[NB][32 * RS];      // R -> S: filter outputs
+    alignas(16) T v[NB][32 * RS];      // R -> S: per-sample mix gains g[t], only while they still move
+    T gval[NB][32];                    // converged mix gains of the tile's 32 filters
+    int gtile[NB];                     // 1: gains in v (per sample);  0: gains in gval (constant)
     unsigned long long x_full[XB], x_empty[XB], u_full[NB], u_empty[NB], v_full[NB], v_empty[NB];
-};
-template <typename T> struct SmemBands : Smem<T> {
-    alignas(16) T y[NB][32 * Cfg<T>::RS];
 };
 
 }  // namespace ws
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
     using namespace ws;
     typedef Ar<T, FMA> A;
     constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
-    typedef typename std::conditional<BANDS, SmemBands<T>, Smem<T>>::type SM;
+    typedef Smem<T> SM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
@@ -162,19 +162,34 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
             const int tn = (int)min((long)TILE, L - k * TILE);
             int tt = 0;
             if (conv) {
-#pragma unroll 4
-                for (; tt + 4 <= tn; tt += 4) {
-                    T xv[4], uv[4];
-                    ld4<T>(xc + tt, xv);
+                // 16 samples per trip; the next 16 inputs are fetched while these are computed
+                T xn[16];
+                if (tn >= 16) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        T fw = A::mul(b0, xv[j]);                       // filterbank.h:178
-                        fw = A::muladd(b1, x1, fw);
-                        fw = A::muladd(b2, x2, fw);
-                        uv[j] = FMA ? fw : A::mul(fw, p);               // strict: u = fl(fw*p); fma: fused in R
-                        x2 = x1; x1 = xv[j];
+                    for (int q = 0; q < 4; q++) ld4<T>(xc + 4 * q, *reinterpret_cast<T(*)[4]>(&xn[4 * q]));
+                }
+                for (; tt + 16 <= tn; tt += 16) {
+                    T xv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) xv[j] = xn[j];
+                    if (tt + 32 <= tn) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) ld4<T>(xc + tt + 16 + 4 * q, *reinterpret_cast<T(*)[4]>(&xn[4 * q]));
                     }
-                    st4<T>(urow + tt, uv);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        T uv[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const T x0 = xv[4 * q + j];
+                            T fw = A::mul(b0, x0);                      // filterbank.h:178
+                            fw = A::muladd(b1, x1, fw);
+                            fw = A::muladd(b2, x2, fw);
+                            uv[j] = FMA ? fw : A::mul(fw, p);           // strict: u = fl(fw*p); fma: fused in R
+                            x2 = x1; x1 = x0;
+                        }
+                        st4<T>(urow + tt + 4 * q, uv);
+                    }
                 }
             }
             for (; tt < tn; tt++) {
@@ -197,6 +212,9 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         if (grp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
     } else if (role == 0) {
         // ---------------- R: the recurrence ----------------
+        // Steady state (gains converged): only the 3-op chain, a2*y2 and the tile traffic stay here;
+        // the y tile goes to S, which applies g.  While g (or p, fma mode) still moves, R also writes
+        // the per-sample gains g[t] and flags the tile.
         const T a1 = ok ? P.par[3 * (size_t)N + n] : (T)0, a2 = ok ? P.par[4 * (size_t)N + n] : (T)0;
         const T gin = ok ? P.par[6 * (size_t)N + n] : (T)0;
         T y1 = ok ? P.state[0 * SN + si] : (T)0, y2 = ok ? P.state[1 * SN + si] : (T)0;
@@ -211,30 +229,37 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
             mbar_wait(&sm.u_full[ub], (unsigned)((k / NB) & 1));
             mbar_wait(&sm.v_empty[ub], (unsigned)(((k / NB) & 1) ^ 1));
             const T* urow = sm.u[ub] + lane * RS;
+            T* yrow = sm.y[ub] + lane * RS;
             T* vrow = sm.v[ub] + lane * RS;
-            T* yrow = BANDS ? (reinterpret_cast<SmemBands<T>&>(sm).y[ub] + lane * RS) : nullptr;
             const int tn = (int)min((long)TILE, L - k * TILE);
             int tt = 0;
-            if (gconv && pconv) {
-                T un[4];
-                if (tn >= 4) ld4<T>(urow, un);
-#pragma unroll 4
-                for (; tt + 4 <= tn; tt += 4) {
-                    T uc[4] = {un[0], un[1], un[2], un[3]};
-                    if (tt + 8 <= tn) ld4<T>(urow + tt + 4, un);       // prefetch the next group
-                    T vv[4], yy[4];
+            const bool lean = gconv && pconv;
+            if (lean) {
+                if (lane == 0) { sm.gtile[ub] = 0; }
+                sm.gval[ub][lane] = g;
+                T t2 = A::mul(a2, y2);
+                if (tn == TILE) {
+                    // whole tile as straight-line code: every LDS/STS has an immediate offset and the
+                    // scheduler is free to hoist the loads far ahead of the serial chain
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        T fb = A::mul(a1, y1);                          // filterbank.h:179
-                        fb = A::muladd(a2, y2, fb);
-                        const T y = FMA ? A::mulsub(uc[j], p, fb) : A::sub(uc[j], fb);     // :178-179
-                        y2 = y1; y1 = y;
-                        yy[j] = y;
-                        vv[j] = A::mul(y, g);                           // :130 product; the sum is S's job
+                    for (int q = 0; q < TILE / 4; q++) {
+                        T uc[4], yy[4];
+                        ld4<T>(urow + 4 * q, uc);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            // filterbank.h:179 fb = fl(fl(a1 y1) + fl(a2 y2)); :178-179 y = fl(u - fb)
+                            const T fb = FMA ? A::muladd(a2, y2, A::mul(a1, y1)) : A::add(A::mul(a1, y1), t2);
+                            const T y = FMA ? A::mulsub(uc[j], p, fb) : A::sub(uc[j], fb);
+                            t2 = A::mul(a2, y1);
+                            y2 = y1; y1 = y;
+                            yy[j] = y;
+                        }
+                        st4<T>(yrow + 4 * q, yy);
                     }
-                    st4<T>(vrow + tt, vv);
-                    if (BANDS) st4<T>(yrow + tt, yy);
+                    tt = TILE;
                 }
+            } else if (lane == 0) {
+                sm.gtile[ub] = 1;
             }
             for (; tt < tn; tt++) {
                 if (!gconv) g = A::muladd(s_g, g, cg);                  // filterbank.h:173
@@ -243,8 +268,8 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
                 fb = A::muladd(a2, y2, fb);
                 const T y = FMA ? A::mulsub(urow[tt], p, fb) : A::sub(urow[tt], fb);
                 y2 = y1; y1 = y;
-                vrow[tt] = A::mul(y, g);
-                if (BANDS) yrow[tt] = y;
+                yrow[tt] = y;
+                if (!lean) vrow[tt] = g;                                // S applies the moving gain g[t]
             }
             if (!gconv) gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
             if (FMA && !pconv) pconv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
@@ -263,21 +288,31 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         for (long k = 0; k < ntiles; k++) {
             const int ub = (int)(k % NB);
             mbar_wait(&sm.v_full[ub], (unsigned)((k / NB) & 1));
-            const T* vt = sm.v[ub];
             const int tn = (int)min((long)TILE, L - k * TILE);
             const long tg = k * TILE;
+            const T* yt = sm.y[ub];
             if (out_row) {
+                // out[t] = sum_l fma(y_l[t], g_l[t], .) in lane order l = 0..31 (filterbank.h:130): the same
+                // function of (y, g) whether the gains still move (g tile) or not (gval), so the sum
+                // does not depend on how the block is split into calls or tiles.
+                const bool moving = sm.gtile[ub] != 0;
+                const T* gt = sm.v[ub];
+                const T* gv = sm.gval[ub];
 #pragma unroll
                 for (int j = 0; j < TILE / 32; j++) {
                     const int t = lane + 32 * j;
                     T sum = (T)0;
+                    if (moving) {
 #pragma unroll 8
-                    for (int l = 0; l < 32; l++) sum += vt[l * RS + t];   // fixed order: deterministic
+                        for (int l = 0; l < 32; l++) sum = A::acc(yt[l * RS + t], gt[l * RS + t], sum);
+                    } else {
+#pragma unroll 8
+                        for (int l = 0; l < 32; l++) sum = A::acc(yt[l * RS + t], gv[l], sum);
+                    }
                     if (t < tn) out_row[tg + t] = sum;
                 }
             }
             if (BANDS) {
-                const T* yt = reinterpret_cast<SmemBands<T>&>(sm).y[ub];
                 for (int r = 0; r < rows; r++) {
                     T* dst = P.bands + ((size_t)s * N + grp * 32 + r) * P.bands_stride + tg;
 #pragma unroll
@@ -295,7 +330,7 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
 
 template <typename T, bool FMA, bool BANDS>
 static hg_status launch_ws(const FbK1Params<T>& P, int groups, cudaStream_t st) {
-    typedef typename std::conditional<BANDS, ws::SmemBands<T>, ws::Smem<T>>::type SM;
+    typedef ws::Smem<T> SM;
     const size_t smem = sizeof(SM);
     auto kern = fb_exact_ws_kernel<T, FMA, BANDS>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
