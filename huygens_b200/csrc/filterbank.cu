@@ -319,6 +319,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.bands = d_bands ? d_bands + t0 : nullptr;
         P.bands_stride = (long)L;
         P.bands_vec = (vec_ok && (t0 % 4 == 0)) ? 1 : 0;
+        P.taps = fb->taps;
         P.N = fb->N;
         P.S = fb->S;
         P.L = (long)len;

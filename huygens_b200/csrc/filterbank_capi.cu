@@ -162,6 +162,16 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     const size_t S = fb->S, N = fb->N;
 
     if (fb->dirty) {
+        // structure of the forward taps over the whole bank (the ws kernel skips exact identities)
+        bool b1_zero = true, antisym = true;
+        for (size_t i = 0; i < N && b1_zero; i++) {
+            double b0, b1, b2;
+            if (fb->dtype == HG_F32) { b0 = par_row<float>(fb, 0)[i]; b1 = par_row<float>(fb, 1)[i]; b2 = par_row<float>(fb, 2)[i]; }
+            else { b0 = par_row<double>(fb, 0)[i]; b1 = par_row<double>(fb, 1)[i]; b2 = par_row<double>(fb, 2)[i]; }
+            if (b1 != 0) b1_zero = false;
+            if (b2 != -b0) antisym = false;
+        }
+        fb->taps = b1_zero ? (antisym ? 2 : 1) : 0;
         HG_CUDA(cudaMemcpyAsync(fb->d_par, fb->h_par, 7 * N * es, cudaMemcpyHostToDevice, st));
         // the pinned shadow may be rewritten by a setter right after we return
         HG_CUDA(cudaStreamSynchronize(st));

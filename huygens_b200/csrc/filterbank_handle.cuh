@@ -16,6 +16,7 @@ struct hg_fb {
     void* h_par = nullptr;       // pinned host shadow of d_par
     void* d_par = nullptr;
     bool dirty = true;
+    int taps = 0;                // structure of the forward taps, detected at upload
     void* d_state = nullptr;
     void* d_xh = nullptr;
     int xh_cur = 0;
@@ -42,6 +43,7 @@ template <typename T> struct FbK1Params {
     T c_p, s_p, c_g, s_g;
     int direct;
     int bands_vec;
+    int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
 };
 
 template <typename T>

@@ -50,6 +50,16 @@ __device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity
         : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (no suspend): used to look ahead from inside the recurrence chain
+__device__ __forceinline__ bool mbar_poll(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity));   // no "memory" clobber: must not fence the unrolled chain
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
     while (!mbar_test(b, parity)) {}
 }
@@ -76,6 +86,17 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
     *reinterpret_cast<double2*>(p + 2) = make_double2(x[2], x[3]);
 }
 
+// 16-byte row fragments: 4 floats or 2 doubles
+template <typename T> __device__ __forceinline__ void ldrow(const float* p, float (&x)[4]) { ld4<float>(p, x); }
+template <typename T> __device__ __forceinline__ void ldrow(const double* p, double (&x)[2]) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    x[0] = a.x; x[1] = a.y;
+}
+template <typename T> __device__ __forceinline__ void strow(float* p, const float (&x)[4]) { st4<float>(p, x); }
+template <typename T> __device__ __forceinline__ void strow(double* p, const double (&x)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(x[0], x[1]);
+}
+
 template <typename T> struct Smem {
     static constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
     alignas(16) T xs[XB][XT];
@@ -89,11 +110,72 @@ template <typename T> struct Smem {
 
 }  // namespace ws
 
+// feed-forward term of one sample.  TAPS: 0 = general b0,b1,b2;  1 = b1 == 0 for every filter;
+// 2 = b1 == 0 and b2 == -b0 (every bank in the reference: {g,0,-g}).  In modes 1/2 the skipped
+// operations are exact identities: fl(b1*x1) = +-0 and x + (+-0) = x, fl((-b0)*x) = -fl(b0*x); only the
+// sign of an exact zero can differ, which no later operation can turn into a nonzero difference.
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ T ws_forward(T b0, T b1, T b2, T x0, T x1, T x2, T& m1, T& m2) {
+    typedef Ar<T, FMA> A;
+    if (TAPS == 2 && !FMA) {
+        const T m0 = A::mul(b0, x0);
+        const T fw = A::sub(m0, m2);       // m2 = fl(b0 * x[t-2])
+        m2 = m1; m1 = m0;
+        return fw;
+    }
+    T fw = A::mul(b0, x0);                                   // filterbank.h:178
+    if (TAPS == 0) fw = A::muladd(b1, x1, fw);
+    fw = A::muladd(b2, x2, fw);
+    return fw;
+}
+
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ void ws_u_tile(const T* __restrict__ xc, T* __restrict__ urow, int tn, T b0, T b1, T b2, T p, T& x1, T& x2, T& m1, T& m2) {
+    typedef Ar<T, FMA> A;
+    constexpr int TILE = ws::Cfg<T>::TILE;
+    if (tn == TILE) {
+        // straight-line tile, 16 samples per block; the next block's inputs are fetched before this
+        // block is computed so the LDS latency hides behind 16 samples of arithmetic
+        T xa[16], xb[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) ws::ld4<T>(xc + 4 * q, *reinterpret_cast<T(*)[4]>(&xa[4 * q]));
+#pragma unroll
+        for (int blk = 0; blk < TILE / 16; blk++) {
+            T(&cur)[16] = (blk & 1) ? xb : xa;
+            T(&nxt)[16] = (blk & 1) ? xa : xb;
+            if (blk + 1 < TILE / 16) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) ws::ld4<T>(xc + 16 * (blk + 1) + 4 * q, *reinterpret_cast<T(*)[4]>(&nxt[4 * q]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                T uv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const T x0 = cur[4 * q + j];
+                    const T fw = ws_forward<T, FMA, TAPS>(b0, b1, b2, x0, x1, x2, m1, m2);
+                    uv[j] = FMA ? fw : A::mul(fw, p);        // strict: u = fl(fw*p); fma: fused in R
+                    x2 = x1; x1 = x0;
+                }
+                ws::st4<T>(urow + 16 * blk + 4 * q, uv);
+            }
+        }
+    } else {
+        for (int tt = 0; tt < tn; tt++) {
+            const T x0 = xc[tt];
+            const T fw = ws_forward<T, FMA, TAPS>(b0, b1, b2, x0, x1, x2, m1, m2);
+            urow[tt] = FMA ? fw : A::mul(fw, p);
+            x2 = x1; x1 = x0;
+        }
+    }
+}
+
 template <typename T, bool FMA, bool BANDS>
 __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
     using namespace ws;
     typedef Ar<T, FMA> A;
     constexpr int TILE = Cfg<T>::TILE, RS = Cfg<T>::RS;
+    constexpr int SPL = TILE / 32;       // samples per S lane: 16 bytes for both dtypes
     typedef Smem<T> SM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -107,8 +189,10 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
     const int n = grp * 32 + lane;
     const bool ok = n < N;
     const size_t SN = (size_t)P.S * N, si = (size_t)s * N + n;
-    const long ntiles = (L + TILE - 1) / TILE;
-    const long nchunks = (L + XT - 1) / XT;
+    // per-tile bookkeeping stays in 32-bit registers: ring slots advance with wrap, no div/mod
+    const int ntiles = (int)((L + TILE - 1) / TILE);
+    const int nchunks = (int)((L + XT - 1) / XT);
+    const int last_tn = (int)(L - (long)(ntiles - 1) * TILE);      // samples in the final tile
     constexpr int TPC = XT / TILE;       // tiles per input chunk
 
     if (threadIdx.x == 0) {
@@ -124,10 +208,11 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
     if (role == 3) {
         // ---------------- L: input loader ----------------
         const T* inp = P.in + (size_t)s * P.in_stride;
-        for (long c = 0; c < nchunks; c++) {
-            const int b = (int)(c % XB);
-            mbar_wait(&sm.x_empty[b], (unsigned)(((c / XB) & 1) ^ 1));
-            const long base = c * XT;
+        int b = 0;
+        unsigned xpar = 0;
+        for (int c = 0; c < nchunks; c++) {
+            mbar_wait(&sm.x_empty[b], xpar ^ 1u);
+            const long base = (long)c * XT;
             const int cnt = (int)min((long)XT, L - base);
             const T* src = inp + base;
             const unsigned bytes = (unsigned)(cnt * sizeof(T));
@@ -141,6 +226,7 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.x_full[b]);
             }
+            if (++b == XB) { b = 0; xpar ^= 1u; }
         }
     } else if (role == 1) {
         // ---------------- U: feed-forward taps and pre-gain ----------------
@@ -150,63 +236,41 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         T p = ok ? P.state[2 * SN + si] : (T)0;
         const T cp = A::mul(P.c_p, pin), s_p = P.s_p;
         T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
+        T m1 = A::mul(b0, x1), m2 = A::mul(b0, x2);          // TAPS == 2: fl(b0*x[t-1]), fl(b0*x[t-2])
+        const int taps = P.taps;
         // strict: U owns the p smoother (u = fl(fw*p)); fma: y = fma(fw, p, -fb) needs p in R instead
         bool conv = FMA ? true : __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
-        for (long k = 0; k < ntiles; k++) {
-            const long c = k / TPC;
-            const int xb = (int)(c % XB), ub = (int)(k % NB);
-            if (k % TPC == 0) mbar_wait(&sm.x_full[xb], (unsigned)((c / XB) & 1));
-            mbar_wait(&sm.u_empty[ub], (unsigned)(((k / NB) & 1) ^ 1));
-            const T* xc = sm.xs[xb] + (k % TPC) * TILE;
+        int xb = 0, ub = 0, kc = 0;
+        unsigned xpar = 0, upar = 0;
+        for (int k = 0; k < ntiles; k++) {
+            if (kc == 0) mbar_wait(&sm.x_full[xb], xpar);
+            mbar_wait(&sm.u_empty[ub], upar ^ 1u);
+            const T* xc = sm.xs[xb] + kc * TILE;
             T* urow = sm.u[ub] + lane * RS;
-            const int tn = (int)min((long)TILE, L - k * TILE);
-            int tt = 0;
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
             if (conv) {
-                // 16 samples per trip; the next 16 inputs are fetched while these are computed
-                T xn[16];
-                if (tn >= 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) ld4<T>(xc + 4 * q, *reinterpret_cast<T(*)[4]>(&xn[4 * q]));
+                if (taps == 2) ws_u_tile<T, FMA, 2>(xc, urow, tn, b0, b1, b2, p, x1, x2, m1, m2);
+                else if (taps == 1) ws_u_tile<T, FMA, 1>(xc, urow, tn, b0, b1, b2, p, x1, x2, m1, m2);
+                else ws_u_tile<T, FMA, 0>(xc, urow, tn, b0, b1, b2, p, x1, x2, m1, m2);
+            } else {
+                for (int tt = 0; tt < tn; tt++) {
+                    p = A::muladd(s_p, p, cp);                          // filterbank.h:172
+                    const T x0 = xc[tt];
+                    const T fw = ws_forward<T, FMA, 0>(b0, b1, b2, x0, x1, x2, m1, m2);
+                    urow[tt] = FMA ? fw : A::mul(fw, p);
+                    x2 = x1; x1 = x0;
                 }
-                for (; tt + 16 <= tn; tt += 16) {
-                    T xv[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) xv[j] = xn[j];
-                    if (tt + 32 <= tn) {
-#pragma unroll
-                        for (int q = 0; q < 4; q++) ld4<T>(xc + tt + 16 + 4 * q, *reinterpret_cast<T(*)[4]>(&xn[4 * q]));
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        T uv[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const T x0 = xv[4 * q + j];
-                            T fw = A::mul(b0, x0);                      // filterbank.h:178
-                            fw = A::muladd(b1, x1, fw);
-                            fw = A::muladd(b2, x2, fw);
-                            uv[j] = FMA ? fw : A::mul(fw, p);           // strict: u = fl(fw*p); fma: fused in R
-                            x2 = x1; x1 = x0;
-                        }
-                        st4<T>(urow + tt + 4 * q, uv);
-                    }
-                }
+                m1 = A::mul(b0, x1); m2 = A::mul(b0, x2);
+                conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
             }
-            for (; tt < tn; tt++) {
-                if (!conv) p = A::muladd(s_p, p, cp);                   // filterbank.h:172
-                const T x0 = xc[tt];
-                T fw = A::mul(b0, x0);
-                fw = A::muladd(b1, x1, fw);
-                fw = A::muladd(b2, x2, fw);
-                urow[tt] = FMA ? fw : A::mul(fw, p);
-                x2 = x1; x1 = x0;
-            }
-            if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
             __syncwarp();
+            const bool chunk_done = (kc == TPC - 1) || (k == ntiles - 1);
             if (lane == 0) {
                 mbar_arrive(&sm.u_full[ub]);
-                if (k % TPC == TPC - 1 || k == ntiles - 1) mbar_arrive(&sm.x_empty[xb]);
+                if (chunk_done) mbar_arrive(&sm.x_empty[xb]);
             }
+            if (++ub == NB) { ub = 0; upar ^= 1u; }
+            if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
         }
         if (ok && !FMA) P.state[2 * SN + si] = p;
         if (grp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
@@ -214,7 +278,9 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         // ---------------- R: the recurrence ----------------
         // Steady state (gains converged): only the 3-op chain, a2*y2 and the tile traffic stay here;
         // the y tile goes to S, which applies g.  While g (or p, fma mode) still moves, R also writes
-        // the per-sample gains g[t] and flags the tile.
+        // the per-sample gains g[t] and flags the tile.  A full tile is straight-line code; the
+        // barriers of the next tile are polled and its first group is fetched inside the chain's
+        // stall slots, so the chain restarts without waiting.
         const T a1 = ok ? P.par[3 * (size_t)N + n] : (T)0, a2 = ok ? P.par[4 * (size_t)N + n] : (T)0;
         const T gin = ok ? P.par[6 * (size_t)N + n] : (T)0;
         T y1 = ok ? P.state[0 * SN + si] : (T)0, y2 = ok ? P.state[1 * SN + si] : (T)0;
@@ -224,57 +290,80 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         const T cg = A::mul(P.c_g, gin), s_g = P.s_g, cp = A::mul(P.c_p, pin), s_p = P.s_p;
         bool gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
         bool pconv = FMA ? __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p) : true;
-        for (long k = 0; k < ntiles; k++) {
-            const int ub = (int)(k % NB);
-            mbar_wait(&sm.u_full[ub], (unsigned)((k / NB) & 1));
-            mbar_wait(&sm.v_empty[ub], (unsigned)(((k / NB) & 1) ^ 1));
+        bool ready = false, have_u0 = false;     // next tile's barriers already seen complete / first group loaded
+        T u0[4] = {(T)0, (T)0, (T)0, (T)0};
+        int ub = 0;
+        unsigned upar = 0;
+        for (int k = 0; k < ntiles; k++) {
+            if (!ready) {
+                mbar_wait(&sm.u_full[ub], upar);
+                mbar_wait(&sm.v_empty[ub], upar ^ 1u);
+            }
             const T* urow = sm.u[ub] + lane * RS;
             T* yrow = sm.y[ub] + lane * RS;
             T* vrow = sm.v[ub] + lane * RS;
-            const int tn = (int)min((long)TILE, L - k * TILE);
-            int tt = 0;
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
             const bool lean = gconv && pconv;
-            if (lean) {
-                if (lane == 0) { sm.gtile[ub] = 0; }
+            const bool more = k + 1 < ntiles;
+            const int nb = (ub + 1 == NB) ? 0 : ub + 1;
+            const unsigned npar = (ub + 1 == NB) ? (upar ^ 1u) : upar;
+            bool next_ready = false, next_u0 = false;
+            bool poll_u = false, poll_v = false;
+            if (lean && tn == TILE) {
+                if (lane == 0) sm.gtile[ub] = 0;
                 sm.gval[ub][lane] = g;
                 T t2 = A::mul(a2, y2);
-                if (tn == TILE) {
-                    // whole tile as straight-line code: every LDS/STS has an immediate offset and the
-                    // scheduler is free to hoist the loads far ahead of the serial chain
+                T first[4];
+                if (have_u0) { first[0] = u0[0]; first[1] = u0[1]; first[2] = u0[2]; first[3] = u0[3]; }
+                else ld4<T>(urow, first);
 #pragma unroll
-                    for (int q = 0; q < TILE / 4; q++) {
-                        T uc[4], yy[4];
-                        ld4<T>(urow + 4 * q, uc);
+                for (int q = 0; q < TILE / 4; q++) {
+                    T uc[4], yy[4];
+                    if (q == 0) { uc[0] = first[0]; uc[1] = first[1]; uc[2] = first[2]; uc[3] = first[3]; }
+                    else ld4<T>(urow + 4 * q, uc);               // hoisted by the scheduler into the chain's stall slots
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            // filterbank.h:179 fb = fl(fl(a1 y1) + fl(a2 y2)); :178-179 y = fl(u - fb)
-                            const T fb = FMA ? A::muladd(a2, y2, A::mul(a1, y1)) : A::add(A::mul(a1, y1), t2);
-                            const T y = FMA ? A::mulsub(uc[j], p, fb) : A::sub(uc[j], fb);
-                            t2 = A::mul(a2, y1);
-                            y2 = y1; y1 = y;
-                            yy[j] = y;
-                        }
-                        st4<T>(yrow + 4 * q, yy);
+                    for (int j = 0; j < 4; j++) {
+                        // filterbank.h:179 fb = fl(fl(a1 y1) + fl(a2 y2)); :178-179 y = fl(u - fb)
+                        const T fb = FMA ? A::muladd(a2, y2, A::mul(a1, y1)) : A::add(A::mul(a1, y1), t2);
+                        const T y = FMA ? A::mulsub(uc[j], p, fb) : A::sub(uc[j], fb);
+                        t2 = A::mul(a2, y1);
+                        y2 = y1; y1 = y;
+                        yy[j] = y;
                     }
-                    tt = TILE;
+                    st4<T>(yrow + 4 * q, yy);
+                    // look ahead: probe the next tile's barriers early, consume the answer late, so the
+                    // probe latency and the first LDS of the next tile sit in the chain's stall slots
+                    if (q == TILE / 4 - 16 && more) {
+                        poll_u = mbar_poll(&sm.u_full[nb], npar);
+                        poll_v = mbar_poll(&sm.v_empty[nb], npar ^ 1u);
+                    }
+                    if (q == TILE / 4 - 5 && more) next_ready = __all_sync(0xffffffffu, poll_u && poll_v);
+                    if (q == TILE / 4 - 4 && next_ready) {
+                        ld4<T>(sm.u[nb] + lane * RS, u0);
+                        next_u0 = true;
+                    }
                 }
-            } else if (lane == 0) {
-                sm.gtile[ub] = 1;
+            } else {
+                if (lane == 0) sm.gtile[ub] = lean ? 0 : 1;
+                sm.gval[ub][lane] = g;
+                for (int tt = 0; tt < tn; tt++) {
+                    if (!gconv) g = A::muladd(s_g, g, cg);              // filterbank.h:173
+                    if (FMA && !pconv) p = A::muladd(s_p, p, cp);       // filterbank.h:172 (fma mode: p lives here)
+                    T fb = A::mul(a1, y1);
+                    fb = A::muladd(a2, y2, fb);
+                    const T y = FMA ? A::mulsub(urow[tt], p, fb) : A::sub(urow[tt], fb);
+                    y2 = y1; y1 = y;
+                    yrow[tt] = y;
+                    if (!lean) vrow[tt] = g;                            // S applies the moving gain g[t]
+                }
+                if (!gconv) gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
+                if (FMA && !pconv) pconv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
             }
-            for (; tt < tn; tt++) {
-                if (!gconv) g = A::muladd(s_g, g, cg);                  // filterbank.h:173
-                if (FMA && !pconv) p = A::muladd(s_p, p, cp);           // filterbank.h:172 (fma mode: p lives here)
-                T fb = A::mul(a1, y1);
-                fb = A::muladd(a2, y2, fb);
-                const T y = FMA ? A::mulsub(urow[tt], p, fb) : A::sub(urow[tt], fb);
-                y2 = y1; y1 = y;
-                yrow[tt] = y;
-                if (!lean) vrow[tt] = g;                                // S applies the moving gain g[t]
-            }
-            if (!gconv) gconv = __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);
-            if (FMA && !pconv) pconv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            ready = next_ready;
+            have_u0 = next_u0;
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sm.u_empty[ub]); mbar_arrive(&sm.v_full[ub]); }
+            ub = nb; upar = npar;
         }
         if (ok) {
             P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[3 * SN + si] = g;
@@ -282,48 +371,58 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         }
     } else {
         // ---------------- S: mixdown over the 32 lanes, per-band rows ----------------
+        // lane owns SPL consecutive samples (16 bytes) of every row: LDS.128 rows, STG.128 out.
+        // out[t] = sum_l fma(y_l[t], g_l[t], .) in lane order l = 0..31 (filterbank.h:130): the same
+        // function of (y, g) whether the gains still move (g tile) or not (gval), so the sum does
+        // not depend on how the block is split into calls or tiles.
         T* out_row = nullptr;
         if (P.out) out_row = P.direct ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
+        const bool out_vec = out_row && ((((uintptr_t)out_row) & 15) == 0);
         const int rows = min(32, N - grp * 32);
-        for (long k = 0; k < ntiles; k++) {
-            const int ub = (int)(k % NB);
-            mbar_wait(&sm.v_full[ub], (unsigned)((k / NB) & 1));
-            const int tn = (int)min((long)TILE, L - k * TILE);
-            const long tg = k * TILE;
-            const T* yt = sm.y[ub];
-            if (out_row) {
-                // out[t] = sum_l fma(y_l[t], g_l[t], .) in lane order l = 0..31 (filterbank.h:130): the same
-                // function of (y, g) whether the gains still move (g tile) or not (gval), so the sum
-                // does not depend on how the block is split into calls or tiles.
-                const bool moving = sm.gtile[ub] != 0;
-                const T* gt = sm.v[ub];
-                const T* gv = sm.gval[ub];
+        int ub = 0;
+        unsigned upar = 0;
+        for (int k = 0; k < ntiles; k++) {
+            mbar_wait(&sm.v_full[ub], upar);
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
+            const long tg = (long)k * TILE;
+            const T* yt = sm.y[ub] + SPL * lane;
+            const T* gt = sm.v[ub] + SPL * lane;
+            const bool moving = sm.gtile[ub] != 0;
+            T acc[SPL];
 #pragma unroll
-                for (int j = 0; j < TILE / 32; j++) {
-                    const int t = lane + 32 * j;
-                    T sum = (T)0;
-                    if (moving) {
+            for (int j = 0; j < SPL; j++) acc[j] = (T)0;
 #pragma unroll 8
-                        for (int l = 0; l < 32; l++) sum = A::acc(yt[l * RS + t], gt[l * RS + t], sum);
-                    } else {
-#pragma unroll 8
-                        for (int l = 0; l < 32; l++) sum = A::acc(yt[l * RS + t], gv[l], sum);
+            for (int l = 0; l < 32; l++) {
+                T yv[SPL], gl[SPL];
+                ldrow<T>(yt + l * RS, yv);
+                if (moving) ldrow<T>(gt + l * RS, gl);
+                else {
+                    const T gc = sm.gval[ub][l];
+#pragma unroll
+                    for (int j = 0; j < SPL; j++) gl[j] = gc;
+                }
+#pragma unroll
+                for (int j = 0; j < SPL; j++) acc[j] = A::acc(yv[j], gl[j], acc[j]);
+                if (BANDS && l < rows) {
+                    T* dst = P.bands + ((size_t)s * N + grp * 32 + l) * P.bands_stride + tg + SPL * lane;
+                    if (P.bands_vec && tn == TILE) strow<T>(dst, yv);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < SPL; j++) if (SPL * lane + j < tn) dst[j] = yv[j];
                     }
-                    if (t < tn) out_row[tg + t] = sum;
                 }
             }
-            if (BANDS) {
-                for (int r = 0; r < rows; r++) {
-                    T* dst = P.bands + ((size_t)s * N + grp * 32 + r) * P.bands_stride + tg;
+            if (out_row) {
+                T* dst = out_row + tg + SPL * lane;
+                if (out_vec && tn == TILE && ((tg * sizeof(T)) & 15) == 0) strow<T>(dst, acc);
+                else {
 #pragma unroll
-                    for (int j = 0; j < TILE / 32; j++) {
-                        const int t = lane + 32 * j;
-                        if (t < tn) dst[t] = yt[r * RS + t];
-                    }
+                    for (int j = 0; j < SPL; j++) if (SPL * lane + j < tn) dst[j] = acc[j];
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.v_empty[ub]);
+            if (++ub == NB) { ub = 0; upar ^= 1u; }
         }
     }
 }
