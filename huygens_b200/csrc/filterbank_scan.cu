@@ -1,13 +1,445 @@
-// filterbank_scan.cu — K2: chunked time-parallel scan of the biquad state recurrence (placeholder
-// until the kernel lands; fails loudly rather than falling back).
+// filterbank_scan.cu — K2: chunked time-parallel scan of the biquad state recurrence.
+//
+// The per-filter recurrence of /root/reference/src/filterbank.h:170-187,
+//     y[t] = p[t] * (b0 x[t] + b1 x[t-1] + b2 x[t-2]) - a1 y[t-1] - a2 y[t-2],
+// is linear in (x, initial state), so a block of L samples splits into C chunks that run
+// concurrently:
+//   1. prepass   the gain smoothers p[t], g[t] do not depend on the signal: one thread per filter
+//                replays the rounded one-pole recursions (same arithmetic mode as the exact
+//                kernels, so the same floating-point fixed points) and records their values at
+//                every chunk boundary.
+//   2. pass 1    every (filter, chunk) lane renders its chunk from ZERO state (chunk 0: from the
+//                handle's true state), adds y*g into the chunk's slice of the bank sum and emits its
+//                end state.
+//   3. carry     per filter, in double: s[c+1] = e[c] + A^Lc s[c], A = [[-a1,-a2],[1,0]] — the 2x2
+//                state-space carry propagation (C steps).
+//   4. pass 2    every (filter, chunk >= 1) lane runs the homogeneous recurrence z from its true start
+//                state s[c] and adds z*g into the same slice; stops once |z| <= 2^-32 (2^-60 for
+//                double) of the start state for every filter of the CTA.
+//   5. reduce    partial sums over filter groups -> out (fixed order, deterministic).
+// The result is NOT bit-identical to the serial loop: the recurrence is evaluated with fused
+// multiply-adds and a different association (zero-state + homogeneous part).  DESIGN.md §5 gives
+// the measured error against the oracle; in double it is far inside 1e-12 of peak, in float it is
+// bounded by the reference's own round-off noise gain (it passes 1e-5 for banks that stay above a
+// few hundred Hz at r = 0.999 and fails below).
+#include <cuda_pipeline.h>
+#include <cmath>
 #include "hg_common.cuh"
 #include "filterbank_handle.cuh"
 
 namespace hg {
-template <typename T>
-hg_status fb_process_scan(hg_fb*, const T*, T*, size_t, cudaStream_t) {
-    return fail(HG_ERR_UNSUPPORTED, "scan mode not built yet");
+
+constexpr int K2_NT = 128;
+constexpr int K2_TILE = 32;
+constexpr int K2_XT = 1024;
+
+template <typename T> struct ScanParams {
+    const T* par;        // [7][N]
+    T* state;            // [4][S][N]
+    const T* xh;         // [S][2]
+    T* xh_out;
+    const T* in;         // [S][L]
+    T* partial;          // [groups][S][L]
+    T* pc;               // [C][N] smoothed pre-gain at chunk starts
+    T* gc;               // [C][N]
+    T* e1;               // [S][C][N] zero-state end states y0[end], y0[end-1]
+    T* e2;
+    T* s1;               // [S][C][N] true start states y[t0-1], y[t0-2]
+    T* s2;
+    int N, S, C;
+    long L, Lc;
+    T c_p, s_p, c_g, s_g;
+};
+
+// ---- 1. smoother prepass ----------------------------------------------------------------------
+template <typename T, bool FMA>
+__global__ void __launch_bounds__(128) scan_prepass(ScanParams<T> P) {
+    typedef Ar<T, FMA> A;
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= P.N) return;
+    const int N = P.N;
+    const size_t SN = (size_t)P.S * N;
+    const T cp = A::mul(P.c_p, P.par[5 * (size_t)N + n]), cg = A::mul(P.c_g, P.par[6 * (size_t)N + n]);
+    // stream 0 carries the smoother state of every stream (they share targets and history)
+    T p = P.state[2 * SN + n], g = P.state[3 * SN + n];
+    long t = 0;
+    for (int c = 0; c < P.C; c++) {
+        const long tc = (long)c * P.Lc;
+        bool moving = true;
+        while (t < tc && moving) {
+            const T pn = A::muladd(P.s_p, p, cp), gn = A::muladd(P.s_g, g, cg);
+            moving = (pn != p) || (gn != g);
+            p = pn; g = gn;
+            t++;
+        }
+        t = tc;     // converged: nothing changes up to the chunk boundary
+        P.pc[(size_t)c * N + n] = p;
+        P.gc[(size_t)c * N + n] = g;
+    }
+    bool moving = true;
+    while (t < P.L && moving) {
+        const T pn = A::muladd(P.s_p, p, cp), gn = A::muladd(P.s_g, g, cg);
+        moving = (pn != p) || (gn != g);
+        p = pn; g = gn;
+        t++;
+    }
+    for (int s = 0; s < P.S; s++) {
+        P.state[2 * SN + (size_t)s * N + n] = p;
+        P.state[3 * SN + (size_t)s * N + n] = g;
+    }
 }
+
+// ---- 2. pass 1: zero-state render of every chunk -------------------------------------------------
+template <typename T, bool FMA, int F>
+__global__ void __launch_bounds__(K2_NT) scan_pass1(ScanParams<T> P) {
+    typedef Ar<T, FMA> A;
+    constexpr int NT = K2_NT, NW = NT / 32, RS = NT + NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);           // [2][XT]
+    T* red = xs + 2 * K2_XT;                           // [2][TILE][RS]
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    const int N = P.N;
+    const size_t SN = (size_t)P.S * N;
+    const long t0 = (long)c * P.Lc;
+    const long len = min(P.Lc, P.L - t0);
+    const int n_base = grp * NT * F;
+
+    T nb0[F], nb1[F], nb2[F], na1[F], na2[F], y1[F], y2[F], p[F], g[F], cp[F], cg[F];
+    bool conv = true;
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        const int n = n_base + f * NT + tid;
+        const bool ok = n < N;
+        nb0[f] = ok ? P.par[0 * (size_t)N + n] : (T)0;
+        nb1[f] = ok ? P.par[1 * (size_t)N + n] : (T)0;
+        nb2[f] = ok ? P.par[2 * (size_t)N + n] : (T)0;
+        na1[f] = ok ? -P.par[3 * (size_t)N + n] : (T)0;
+        na2[f] = ok ? -P.par[4 * (size_t)N + n] : (T)0;
+        cp[f] = A::mul(P.c_p, ok ? P.par[5 * (size_t)N + n] : (T)0);
+        cg[f] = A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0);
+        p[f] = ok ? P.pc[(size_t)c * N + n] : (T)0;
+        g[f] = ok ? P.gc[(size_t)c * N + n] : (T)0;
+        // chunk 0 continues from the handle's true state; later chunks start from zero
+        y1[f] = (ok && c == 0) ? P.state[0 * SN + (size_t)s * N + n] : (T)0;
+        y2[f] = (ok && c == 0) ? P.state[1 * SN + (size_t)s * N + n] : (T)0;
+        conv = conv && (A::muladd(P.s_p, p[f], cp[f]) == p[f]) && (A::muladd(P.s_g, g[f], cg[f]) == g[f]);
+    }
+    const T* inp = P.in + (size_t)s * P.L + t0;
+    T x1, x2;
+    if (c == 0) { x1 = P.xh[2 * s]; x2 = P.xh[2 * s + 1]; }
+    else { x1 = inp[-1]; x2 = (t0 >= 2) ? inp[-2] : P.xh[2 * s]; }
+
+    const long nchunks = (len + K2_XT - 1) / K2_XT;
+    auto stage = [&](long k) {
+        const long base = k * K2_XT;
+        const int cnt = (int)min((long)K2_XT, len - base);
+        T* dst = xs + (k & 1) * K2_XT;
+        for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, inp + base + i, sizeof(T));
+        __pipeline_commit();
+    };
+    if (nchunks > 0) stage(0);
+    T* out_row = P.partial + ((size_t)grp * P.S + s) * (size_t)P.L + t0;
+    long tile_idx = 0;
+    int all_conv = 0;
+    for (long k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks) { stage(k + 1); __pipeline_wait_prior(1); }
+        else __pipeline_wait_prior(0);
+        all_conv = __syncthreads_and(conv);
+        const int cnt = (int)min((long)K2_XT, len - k * K2_XT);
+        const T* xc = xs + (k & 1) * K2_XT;
+        for (int tt0 = 0; tt0 < cnt; tt0 += K2_TILE, tile_idx++) {
+            const int tn = min(K2_TILE, cnt - tt0);
+            T* rb = red + (tile_idx & 1) * (K2_TILE * RS);
+            if (all_conv) {
+                // steady gains: fold p into the forward taps
+                T bp0[F], bp1[F], bp2[F];
+#pragma unroll
+                for (int f = 0; f < F; f++) { bp0[f] = nb0[f] * p[f]; bp1[f] = nb1[f] * p[f]; bp2[f] = nb2[f] * p[f]; }
+#pragma unroll 4
+                for (int tt = 0; tt < tn; tt++) {
+                    const T x0 = xc[tt0 + tt];
+                    T acc = (T)0;
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        T u = bp2[f] * x2;
+                        u = fma(bp1[f], x1, u);
+                        u = fma(bp0[f], x0, u);
+                        const T t = fma(na2[f], y2[f], u);
+                        const T y = fma(na1[f], y1[f], t);
+                        y2[f] = y1[f]; y1[f] = y;
+                        acc = fma(y, g[f], acc);
+                    }
+                    x2 = x1; x1 = x0;
+                    rb[tt * RS + tid] = acc;
+                }
+            } else {
+                for (int tt = 0; tt < tn; tt++) {
+                    const T x0 = xc[tt0 + tt];
+                    T acc = (T)0;
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        p[f] = A::muladd(P.s_p, p[f], cp[f]);
+                        g[f] = A::muladd(P.s_g, g[f], cg[f]);
+                        T u = nb2[f] * x2;
+                        u = fma(nb1[f], x1, u);
+                        u = fma(nb0[f], x0, u);
+                        const T t = fma(na2[f], y2[f], u * p[f]);
+                        const T y = fma(na1[f], y1[f], t);
+                        y2[f] = y1[f]; y1[f] = y;
+                        acc = fma(y, g[f], acc);
+                    }
+                    x2 = x1; x1 = x0;
+                    rb[tt * RS + tid] = acc;
+                }
+                conv = true;
+#pragma unroll
+                for (int f = 0; f < F; f++)
+                    conv = conv && (A::muladd(P.s_p, p[f], cp[f]) == p[f]) && (A::muladd(P.s_g, g[f], cg[f]) == g[f]);
+            }
+            all_conv = __syncthreads_and(conv);
+            cta_tile_reduce<T, NT>(rb, tn, out_row + k * K2_XT + tt0);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        const int n = n_base + f * NT + tid;
+        if (n < N) {
+            const size_t i = ((size_t)s * P.C + c) * N + n;
+            P.e1[i] = y1[f];
+            P.e2[i] = y2[f];
+        }
+    }
+    if (grp == 0 && c == P.C - 1 && tid == 0 && len > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+}
+
+// ---- 3. carry: 2x2 state-space propagation in double -------------------------------------------------
+// double-double helpers: A^n by repeated squaring loses ~log2(n) * cond(A^n) digits (cond ~ 1/theta
+// for a resonator at theta rad/sample), which at 27.5 Hz and n ~ 4e4 would eat the 1e-12 budget in
+// plain double; in double-double the carry matrix is exact to far below one double ulp.
+struct dd { double h, l; };
+__device__ __forceinline__ dd dd_make(double h) { dd r; r.h = h; r.l = 0.0; return r; }
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    const double s = __dadd_rn(a.h, b.h);
+    const double bb = __dsub_rn(s, a.h);
+    double e = __dadd_rn(__dsub_rn(a.h, __dsub_rn(s, bb)), __dsub_rn(b.h, bb));
+    e = __dadd_rn(e, __dadd_rn(a.l, b.l));
+    dd r;
+    r.h = __dadd_rn(s, e);
+    r.l = __dsub_rn(e, __dsub_rn(r.h, s));
+    return r;
+}
+__device__ __forceinline__ dd dd_mul(dd a, dd b) {
+    const double p = __dmul_rn(a.h, b.h);
+    double e = __fma_rn(a.h, b.h, -p);
+    e = __dadd_rn(e, __dadd_rn(__dmul_rn(a.h, b.l), __dmul_rn(a.l, b.h)));
+    dd r;
+    r.h = __dadd_rn(p, e);
+    r.l = __dsub_rn(e, __dsub_rn(r.h, p));
+    return r;
+}
+// A = [[-a1, -a2], [1, 0]];  M = A^e (row-major 2x2) by repeated squaring in double-double
+__device__ __forceinline__ void mat2_pow(double a1, double a2, long e, dd (&M)[4]) {
+    dd B[4] = {dd_make(-a1), dd_make(-a2), dd_make(1.0), dd_make(0.0)};
+    M[0] = dd_make(1.0); M[1] = dd_make(0.0); M[2] = dd_make(0.0); M[3] = dd_make(1.0);
+    while (e > 0) {
+        if (e & 1) {
+            const dd r0 = dd_add(dd_mul(M[0], B[0]), dd_mul(M[1], B[2])), r1 = dd_add(dd_mul(M[0], B[1]), dd_mul(M[1], B[3]));
+            const dd r2 = dd_add(dd_mul(M[2], B[0]), dd_mul(M[3], B[2])), r3 = dd_add(dd_mul(M[2], B[1]), dd_mul(M[3], B[3]));
+            M[0] = r0; M[1] = r1; M[2] = r2; M[3] = r3;
+        }
+        const dd q0 = dd_add(dd_mul(B[0], B[0]), dd_mul(B[1], B[2])), q1 = dd_add(dd_mul(B[0], B[1]), dd_mul(B[1], B[3]));
+        const dd q2 = dd_add(dd_mul(B[2], B[0]), dd_mul(B[3], B[2])), q3 = dd_add(dd_mul(B[2], B[1]), dd_mul(B[3], B[3]));
+        B[0] = q0; B[1] = q1; B[2] = q2; B[3] = q3;
+        e >>= 1;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) scan_carry(ScanParams<T> P) {
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= P.N) return;
+    const int N = P.N, C = P.C;
+    const size_t SN = (size_t)P.S * N;
+    const double a1 = (double)P.par[3 * (size_t)N + n], a2 = (double)P.par[4 * (size_t)N + n];
+    dd M[4];
+    mat2_pow(a1, a2, P.Lc, M);
+    // chunk 0 was rendered from the true state: its end state is already the true one
+    double t1 = (double)P.e1[((size_t)s * C + 0) * N + n], t2 = (double)P.e2[((size_t)s * C + 0) * N + n];
+    for (int c = 1; c < C; c++) {
+        const size_t i = ((size_t)s * C + c) * N + n;
+        P.s1[i] = (T)t1;
+        P.s2[i] = (T)t2;
+        const long len = min(P.Lc, P.L - (long)c * P.Lc);
+        dd Mc[4];
+        if (len == P.Lc) { Mc[0] = M[0]; Mc[1] = M[1]; Mc[2] = M[2]; Mc[3] = M[3]; }
+        else mat2_pow(a1, a2, len, Mc);
+        // state vector (y[t-1], y[t-2]); after `len` steps: A^len s + zero-state end
+        const dd v1 = dd_make(t1), v2 = dd_make(t2);
+        const dd z1 = dd_add(dd_add(dd_mul(Mc[0], v1), dd_mul(Mc[1], v2)), dd_make((double)P.e1[i]));
+        const dd z2 = dd_add(dd_add(dd_mul(Mc[2], v1), dd_mul(Mc[3], v2)), dd_make((double)P.e2[i]));
+        t1 = z1.h;
+        t2 = z2.h;
+    }
+    P.state[0 * SN + (size_t)s * N + n] = (T)t1;
+    P.state[1 * SN + (size_t)s * N + n] = (T)t2;
+}
+
+// ---- 4. pass 2: homogeneous correction from the true start states ---------------------------------------
+template <typename T, bool FMA, int F>
+__global__ void __launch_bounds__(K2_NT) scan_pass2(ScanParams<T> P) {
+    typedef Ar<T, FMA> A;
+    constexpr int NT = K2_NT, NW = NT / 32, RS = NT + NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* red = reinterpret_cast<T*>(smem_raw);          // [2][TILE][RS]
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x, c = blockIdx.y + 1, s = blockIdx.z;
+    const int N = P.N;
+    const long t0 = (long)c * P.Lc;
+    const long len = min(P.Lc, P.L - t0);
+    const int n_base = grp * NT * F;
+    T na1[F], na2[F], z1[F], z2[F], g[F], cg[F];
+    T zmax = (T)0;
+    bool conv = true;
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        const int n = n_base + f * NT + tid;
+        const bool ok = n < N;
+        na1[f] = ok ? -P.par[3 * (size_t)N + n] : (T)0;
+        na2[f] = ok ? -P.par[4 * (size_t)N + n] : (T)0;
+        cg[f] = A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0);
+        g[f] = ok ? P.gc[(size_t)c * N + n] : (T)0;
+        const size_t i = ((size_t)s * P.C + c) * N + n;
+        z1[f] = ok ? P.s1[i] : (T)0;
+        z2[f] = ok ? P.s2[i] : (T)0;
+        zmax = fmax(zmax, fmax(fabs(z1[f]), fabs(z2[f])));
+        conv = conv && (A::muladd(P.s_g, g[f], cg[f]) == g[f]);
+    }
+    // below this the correction cannot change the sum at the stated tolerance
+    const T floor_rel = sizeof(T) == 4 ? (T)2.3283064365386963e-10 : (T)8.673617379884035e-19;
+    const T zfloor = zmax * floor_rel;
+    T* out_row = P.partial + ((size_t)grp * P.S + s) * (size_t)P.L + t0;
+    long tile_idx = 0;
+    for (long tt0 = 0; tt0 < len; tt0 += K2_TILE, tile_idx++) {
+        const int tn = (int)min((long)K2_TILE, len - tt0);
+        T* rb = red + (tile_idx & 1) * (K2_TILE * RS);
+        T live = (T)0;
+#pragma unroll 4
+        for (int tt = 0; tt < tn; tt++) {
+            T acc = (T)0;
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                if (!conv) g[f] = A::muladd(P.s_g, g[f], cg[f]);
+                const T z = fma(na1[f], z1[f], na2[f] * z2[f]);
+                z2[f] = z1[f]; z1[f] = z;
+                acc = fma(z, g[f], acc);
+            }
+            rb[tt * RS + tid] = acc;
+        }
+        if (!conv) {
+            conv = true;
+#pragma unroll
+            for (int f = 0; f < F; f++) conv = conv && (A::muladd(P.s_g, g[f], cg[f]) == g[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < F; f++) live = fmax(live, fmax(fabs(z1[f]), fabs(z2[f])));
+        const int any_live = __syncthreads_or(live > zfloor);
+        // read-modify-write of this CTA's own slice (pass 1 wrote it earlier on the same stream)
+        {
+            constexpr int SPW = 32 / NW;
+            const int lane = tid & 31, warp = tid >> 5;
+            const int ls = lane / NW, jq = lane % NW;
+            const int t = warp * SPW + ls;
+            const T* row = rb + t * RS + jq;
+            T sum = (T)0;
+            if (t < tn) {
+#pragma unroll 8
+                for (int i = 0; i < 32; i++) sum += row[i * NW];
+            }
+#pragma unroll
+            for (int o = NW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (jq == 0 && t < tn) out_row[tt0 + t] += sum;
+        }
+        if (!any_live) break;
+    }
+}
+
+// ---- 5. reduce -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scan_reduce(const T* __restrict__ partial, T* __restrict__ out, int groups, int S, long L) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= L) return;
+    T sum = (T)0;
+    for (int g = 0; g < groups; g++) sum += partial[((size_t)g * S + s) * (size_t)L + i];
+    out[(size_t)s * L + i] = sum;
+}
+
+template <typename T, bool FMA, int F>
+static hg_status scan_launch(hg_fb* fb, ScanParams<T>& P, int groups, T* d_out, cudaStream_t st) {
+    constexpr int NW = K2_NT / 32;
+    const size_t smem1 = sizeof(T) * (2 * K2_XT + 2 * K2_TILE * (K2_NT + NW));
+    const size_t smem2 = sizeof(T) * (2 * K2_TILE * (K2_NT + NW));
+    auto k1 = scan_pass1<T, FMA, F>;
+    auto k2 = scan_pass2<T, FMA, F>;
+    if (smem1 > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    if (smem2 > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    scan_prepass<T, FMA><<<(P.N + 127) / 128, 128, 0, st>>>(P);
+    k1<<<dim3(groups, P.C, P.S), K2_NT, smem1, st>>>(P);
+    scan_carry<T><<<dim3((P.N + 127) / 128, P.S), 128, 0, st>>>(P);
+    fb->last_launches += 3;
+    if (P.C > 1) {
+        k2<<<dim3(groups, P.C - 1, P.S), K2_NT, smem2, st>>>(P);
+        fb->last_launches++;
+    }
+    scan_reduce<T><<<dim3((unsigned)((P.L + 255) / 256), P.S), 256, 0, st>>>(P.partial, d_out, groups, P.S, P.L);
+    fb->last_launches++;
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}
+
+template <typename T>
+hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st) {
+    if (!d_out) return fail(HG_ERR_INVALID, "scan mode needs out_sum");
+    const int N = fb->N, S = fb->S;
+    const int F = (sizeof(T) == 4) ? 8 : 4;
+    // enough lanes for ~2 warps per scheduler; chunks are multiples of the input staging size
+    const long want_threads = (long)fb->sm_count * 4 * 32 * 2;
+    long C = (want_threads * F + (long)S * N - 1) / ((long)S * N);
+    if (fb->force_chunks > 0) C = fb->force_chunks;
+    if (C < 1) C = 1;
+    long Lc = ((long)L + C - 1) / C;
+    Lc = ((Lc + K2_XT - 1) / K2_XT) * K2_XT;
+    if (Lc < 4 * K2_XT && fb->force_chunks <= 0) Lc = 4 * K2_XT;
+    C = ((long)L + Lc - 1) / Lc;
+    const int groups = (N + K2_NT * F - 1) / (K2_NT * F);
+    fb->last_F = F;
+    fb->last_ctas = (int)(groups * C * S);
+    // scratch: partial [groups][S][L]; pc, gc [C][N]; e1,e2,s1,s2 [S][C][N]
+    const size_t n_partial = (size_t)groups * S * L;
+    const size_t n_cn = (size_t)C * N, n_scn = (size_t)S * C * N;
+    HG_TRY(fb->scan_a.reserve(n_partial * sizeof(T)));
+    HG_TRY(fb->scan_b.reserve((2 * n_cn + 4 * n_scn) * sizeof(T)));
+    ScanParams<T> P;
+    P.par = (const T*)fb->d_par;
+    P.state = (T*)fb->d_state;
+    P.xh = (const T*)fb->d_xh + (size_t)fb->xh_cur * 2 * S;
+    P.xh_out = (T*)fb->d_xh + (size_t)(fb->xh_cur ^ 1) * 2 * S;
+    fb->xh_cur ^= 1;
+    P.in = d_in;
+    P.partial = (T*)fb->scan_a.p;
+    T* b = (T*)fb->scan_b.p;
+    P.pc = b; P.gc = b + n_cn;
+    P.e1 = b + 2 * n_cn; P.e2 = P.e1 + n_scn; P.s1 = P.e2 + n_scn; P.s2 = P.s1 + n_scn;
+    P.N = N; P.S = S; P.C = (int)C; P.L = (long)L; P.Lc = Lc;
+    P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
+    const bool fma = fb->arith == HG_ARITH_FMA;
+    if (sizeof(T) == 4) return fma ? scan_launch<T, true, 8>(fb, P, groups, d_out, st) : scan_launch<T, false, 8>(fb, P, groups, d_out, st);
+    return fma ? scan_launch<T, true, 4>(fb, P, groups, d_out, st) : scan_launch<T, false, 4>(fb, P, groups, d_out, st);
+}
+
 template hg_status fb_process_scan<float>(hg_fb*, const float*, float*, size_t, cudaStream_t);
 template hg_status fb_process_scan<double>(hg_fb*, const double*, double*, size_t, cudaStream_t);
+
 }  // namespace hg
