@@ -1,0 +1,41 @@
+// banks_demo.cpp — exercises the drop-in Oscbank / RMSbank / FFilterbank per-sample APIs the way
+// tests/rmsbank.cpp and tests/harmbank.cpp chain them (osc() -> rms(...) ; tick()), printing values
+// for the pytest parity check.   banks_demo <ticks>
+#include "../include/huygens/filterbank.h"
+#include "../include/huygens/oscbank.h"
+#include "../include/huygens/rmsbank.h"
+
+using namespace soundmath;
+
+static double softclip(double x) { return x > 0.125 ? 0.125 : (x < -0.125 ? -0.125 : x); }
+
+int main(int argc, char** argv) {
+    const int ticks = argc > 1 ? std::atoi(argv[1]) : 64;
+    try {
+        Oscbank<double, 8> osc;
+        RMSbank<double, 8> rms(16);
+        FFilterbank<double, 4, 2> F(0.001, 1);
+        for (int i = 0; i < 8; i++) osc.freqmod(i, 110.0 * (i + 1));
+        osc.freqmod(99, 1.0);       // ignored, oscbank.h:51
+        osc.open();
+        osc.deactivate({3});
+        for (int i = 0; i < 4; i++) F.coefficients(i, {0.5, 0, -0.5}, {-1.6 + 0.1 * i, 0.81});
+        F.open();
+        F.boost(std::vector<double>(4, 1.0));
+        for (int t = 0; t < ticks; t++) {
+            const auto* ph = osc();
+            const auto* env = rms(ph);
+            const double first = (*env)(0);
+            const double again = (*rms(ph))(0);              // second call in the tick: sqrt applied twice (rmsbank.h:64)
+            const std::complex<double> m = osc.mixdown();
+            const double y = F(m.real());
+            const double yd = F(m.real(), &softclip);
+            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd);
+            osc.tick(); rms.tick(); F.tick();
+        }
+    } catch (const cuda_error& e) {
+        std::fprintf(stderr, "huygens_cuda error %d: %s\n", e.status, e.what());
+        return 1;
+    }
+    return 0;
+}

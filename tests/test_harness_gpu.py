@@ -1,0 +1,90 @@
+"""The C++ host side: drop-in templates (include/huygens/*.h) and the offline render harness, built
+with g++ against libhuygens_cuda.so, checked against the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+from huygens_b200 import design
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness():
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "harness")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return os.path.join(ROOT, "harness")
+
+
+def _resynthesis_oracle(N, dtype, x):
+    freqs, fwd, back = design.resynthesis_bank(N)
+    fb = oracle.Filterbank(2, N, 0.1, 1.0, dtype=dtype)
+    for n in range(N):
+        fb.coefficients(n, fwd[n], back[n])
+    fb.boost(np.ones(N))
+    fb.open()
+    return fb.process(x.astype(dtype))
+
+
+@pytest.mark.parametrize("flags,dtype", [(["--double"], np.float64), ([], np.float32),
+                                         (["--double", "--per-sample", "--bsize", "64"], np.float64)])
+def test_render_harness_matches_oracle(harness, tmp_path, flags, dtype, oracle_lib):
+    N, seconds = 64, 0.25 if "--per-sample" not in flags else 0.02
+    out = tmp_path / "out.f32"
+    r = subprocess.run([os.path.join(harness, "render"), "--filters", str(N), "--seconds", str(seconds),
+                        "--input", "white", "--out", str(out)] + flags, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    L = int(seconds * 48000)
+    assert info["frames"] == L and info["filters"] == N
+    got = np.fromfile(out, dtype=np.float32)
+    x = design.white_noise(L, dtype=np.float32)          # the harness generator must be the same stream
+    ref = _resynthesis_oracle(N, dtype, x)
+    assert rel_err(got, ref.astype(np.float32)) <= 2e-6
+
+
+def test_render_harness_c1_full(harness, tmp_path, oracle_lib):
+    """BASELINE configs[0]: Filterbank<double>, 64 resonant band-passes, 10 s of 48 kHz white noise."""
+    out = tmp_path / "c1.f32"
+    r = subprocess.run([os.path.join(harness, "render"), "--filters", "64", "--seconds", "10", "--double",
+                        "--bsize", "1024", "--out", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(out, dtype=np.float32)
+    ref = _resynthesis_oracle(64, np.float64, design.white_noise(480000, dtype=np.float32))
+    assert rel_err(got, ref.astype(np.float32)) <= 2e-6
+
+
+def test_dropin_per_sample_banks(harness, oracle_lib):
+    ticks = 80
+    r = subprocess.run([os.path.join(harness, "banks_demo"), str(ticks)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+    assert got.shape == (ticks, 6)
+    osc = oracle.Oscbank(8)
+    for i in range(8):
+        osc.freqmod(i, 110.0 * (i + 1))
+    osc.open()
+    osc.deactivate([3])
+    mix, ph = osc.process(ticks, phases=True)
+    assert np.array_equal(got[:, 0], mix.real) and np.array_equal(got[:, 1], mix.imag)
+    zre, zim = np.ascontiguousarray(ph.real.T), np.ascontiguousarray(ph.imag.T)
+    first = oracle.RMSbank(8, 16).process(zre, zim)
+    again = oracle.RMSbank(8, 16).process(zre, zim, calls_per_tick=2)
+    assert np.array_equal(got[:, 2], first[0]) and np.array_equal(got[:, 3], again[0])
+    F = oracle.Filterbank(2, 4, 0.001, 1.0, fixed=True)
+    for i in range(4):
+        F.coefficients(i, [0.5, 0, -0.5], [-1.6 + 0.1 * i, 0.81])
+    F.open()
+    F.boost(np.ones(4))
+    for t in range(ticks):
+        y, bands = F.process(mix.real[t:t + 1], bands=True)
+        _, g = F.smoothed()
+        assert abs(got[t, 4] - y[0]) <= 1e-12 * max(1.0, abs(y[0]))
+        clipped = np.clip(bands[:, 0] * g, -0.125, 0.125).sum()
+        assert abs(got[t, 5] - clipped) <= 1e-12 * max(1.0, abs(clipped))
