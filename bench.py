@@ -33,6 +33,8 @@ SLOTS_PER_FILTER_SAMPLE = 11        # 11 mul + 7 add, every add fusable: SURVEY.
 WORKLOADS = {
     # name: (filters per GPU, seconds, f_lo, f_hi, r, k_p, k_g, input)
     "c2": dict(N=4096, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
+    # BASELINE configs[2] (65,536 filters; a parity/scaling case, not the headline): 10 s blocks
+    "c3": dict(N=65536, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
 }
 
 
@@ -47,13 +49,15 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--seconds", type=float, default=None, help="override block length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scan", action="store_true", help="skip the scan-mode side measurement")
     return ap.parse_args()
 
 
 def bank_params(w, rank, world):
     from huygens_b200 import design
-    N = w["N"]
-    freqs = design.log_spaced(N * world, w["f_lo"], w["f_hi"])[rank * N:(rank + 1) * N]
+    from huygens_b200.sharding import filter_range
+    lo, hi = filter_range(w["N"] * world, rank, world)     # weak scaling: N filters per GPU
+    freqs = design.log_spaced(w["N"] * world, w["f_lo"], w["f_hi"])[lo:hi]
     return design.resonator_bank(freqs, w["r"])
 
 
@@ -84,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -275,6 +279,28 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = tt.item()
 
+    # side measurement (N = 1 only): the same block through the time-parallel scan, whose result is
+    # tolerance-bounded instead of bit-identical
+    scan_info = None
+    if world == 1 and args.mode == "exact" and not args.no_scan:
+        out_exact = out.clone()
+        for _ in range(3):
+            fb.process(x, out=out, mode="scan")
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            sev[i][0].record()
+            fb.process(x, out=out, mode="scan")
+            sev[i][1].record()
+        torch.cuda.synchronize()
+        t_scan = sum(a.elapsed_time(b) for a, b in sev) * 1e-3 / args.steps
+        fb.process(x, out=out_exact, mode="exact")
+        fb.process(x, out=out, mode="scan")
+        diff = (out.double() - out_exact.double()).abs().max().item() / out_exact.double().abs().max().item()
+        scan_info = {"value": float(N) * L / t_scan, "unit": "filter-samples/s", "ms_per_step": t_scan * 1e3,
+                     "roofline_frac": float(N) * L / t_scan * SLOTS_PER_FILTER_SAMPLE / peak["slots_per_s"],
+                     "max_abs_diff_vs_exact_rel_peak": diff,
+                     "note": "not bit-identical; measured error vs the oracle in profiles/scan_error_r1.json and DESIGN.md §5"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -299,6 +325,8 @@ def main():
                      "kernel_ms": t_kernel / args.steps * 1e3, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
                      "ctas": info["ctas"]},
     }
+    if scan_info:
+        line["scan"] = scan_info
     if not args.no_cpu_baseline:
         n_s = 3 * SR
         v, dt = cpu_baseline(w, dtype, n_s, 1)
