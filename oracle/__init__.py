@@ -211,3 +211,157 @@ class RMSbank(_Base):
         out = np.empty((N, L), self.dtype)
         self._f("hgo_rms_process")(self._h, _ptr(zre), _ptr(zim), _ptr(out), L, calls_per_tick)
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the UNMODIFIED reference headers compiled against oracle/shim (see ref_capi.cpp).
+# Used only to pin the restatement above (tests/test_oracle_vs_ref.py).
+# ---------------------------------------------------------------------------------------------
+_REF = None
+REF_FIXED_N = (4, 16, 96)
+REF_OSC_N = (1, 8, 96)
+REF_RMS_N = (1, 8, 40)
+
+
+def ref_lib():
+    """Returns the ctypes handle of oracle/_ref/libhuygens_ref.so or None if it was never built
+    (it is built where /root/reference exists and travels to the GPU box as a binary)."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libhuygens_ref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/src"):
+                build()
+            if not os.path.exists(path):
+                return None
+        _REF = C.CDLL(path)
+        vp, i, d, lg = C.c_void_p, C.c_int, C.c_double, C.c_long
+        sig = {
+            "hgr_relaxation": (d, [d]),
+            "hgr_fb_create": (vp, [i, i, i, i, d, d]), "hgr_fb_destroy": (None, [vp]),
+            "hgr_fb_coefficients": (None, [vp, i, vp, i, vp, i]), "hgr_fb_boost": (None, [vp, i, i, vp]),
+            "hgr_fb_mix": (None, [vp, i, i, vp]), "hgr_fb_open": (None, [vp]),
+            "hgr_fb_process": (None, [vp, vp, vp, vp, lg]), "hgr_fb_get_smoothed": (None, [vp, vp, vp]),
+            "hgr_osc_create": (vp, [i, i]), "hgr_osc_destroy": (None, [vp]), "hgr_osc_freqmod": (None, [vp, i, d]),
+            "hgr_osc_open": (None, [vp]), "hgr_osc_close": (None, [vp]), "hgr_osc_activate": (None, [vp, vp, i, i]),
+            "hgr_osc_active_count": (i, [vp]), "hgr_osc_process": (None, [vp, vp, vp, lg]),
+            "hgr_osc_get_phases": (None, [vp, vp]),
+            "hgr_rms_create": (vp, [i, i, i]), "hgr_rms_destroy": (None, [vp]),
+            "hgr_rms_process": (None, [vp, vp, vp, vp, lg, i]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(_REF, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _REF
+
+
+class RefFilterbank:
+    """soundmath::Filterbank<T> (fixed=False) or FFilterbank<T,N,2> (fixed=True, N in REF_FIXED_N) of
+    the reference itself, driven through the callers' loop."""
+
+    def __init__(self, order, N=1, k_p=0.1, k_g=1.0, dtype=np.float64, fixed=False):
+        self.dtype, self.N = np.dtype(dtype), N
+        self._h = ref_lib().hgr_fb_create(DTYPES[self.dtype], int(fixed), order, N, k_p, k_g)
+        if not self._h:
+            raise ValueError("this FFilterbank<T,N,order> is not instantiated in ref_capi.cpp")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().hgr_fb_destroy(self._h)
+            self._h = None
+
+    def _arr(self, v):
+        return np.ascontiguousarray(np.asarray(v, dtype=np.float64).astype(self.dtype))
+
+    def coefficients(self, n, forward, back):
+        f, b = self._arr(forward), self._arr(back)
+        ref_lib().hgr_fb_coefficients(self._h, n, _ptr(f), len(f), _ptr(b), len(b))
+
+    def boost(self, a, value=None):
+        v = self._arr(a)[: self.N] if value is None else self._arr([value])
+        ref_lib().hgr_fb_boost(self._h, 0 if value is None else int(a), len(v), _ptr(v))
+
+    def mix(self, a, value=None):
+        v = self._arr(a)[: self.N] if value is None else self._arr([value])
+        ref_lib().hgr_fb_mix(self._h, 0 if value is None else int(a), len(v), _ptr(v))
+
+    def open(self):
+        ref_lib().hgr_fb_open(self._h)
+
+    def process(self, x, bands=False):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        out = np.empty(len(x), self.dtype)
+        bd = np.empty((self.N, len(x)), self.dtype) if bands else None
+        ref_lib().hgr_fb_process(self._h, _ptr(x), _ptr(out), _ptr(bd), len(x))
+        return (out, bd) if bands else out
+
+    def smoothed(self):
+        p, g = np.empty(self.N, self.dtype), np.empty(self.N, self.dtype)
+        ref_lib().hgr_fb_get_smoothed(self._h, _ptr(p), _ptr(g))
+        return p, g
+
+
+class RefOscbank:
+    def __init__(self, N, dtype=np.float64):
+        self.dtype, self.N = np.dtype(dtype), N
+        self._h = ref_lib().hgr_osc_create(DTYPES[self.dtype], N)
+        if not self._h:
+            raise ValueError("this Oscbank<T,N> is not instantiated in ref_capi.cpp")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().hgr_osc_destroy(self._h)
+            self._h = None
+
+    def freqmod(self, i, f):
+        ref_lib().hgr_osc_freqmod(self._h, int(i), float(f))
+
+    def open(self):
+        ref_lib().hgr_osc_open(self._h)
+
+    def close(self):
+        ref_lib().hgr_osc_close(self._h)
+
+    def activate(self, idx):
+        a = np.ascontiguousarray(idx, dtype=np.int32)
+        ref_lib().hgr_osc_activate(self._h, _ptr(a), len(a), 1)
+
+    def deactivate(self, idx):
+        a = np.ascontiguousarray(idx, dtype=np.int32)
+        ref_lib().hgr_osc_activate(self._h, _ptr(a), len(a), 0)
+
+    def active_count(self):
+        return ref_lib().hgr_osc_active_count(self._h)
+
+    def process(self, L, phases=False):
+        cdt = np.complex64 if self.dtype == np.float32 else np.complex128
+        mix = np.empty(L, cdt)
+        ph = np.empty((L, self.N), cdt) if phases else None
+        ref_lib().hgr_osc_process(self._h, _ptr(mix), _ptr(ph), L)
+        return (mix, ph) if phases else mix
+
+    def phases(self):
+        p = np.empty(self.N, np.complex64 if self.dtype == np.float32 else np.complex128)
+        ref_lib().hgr_osc_get_phases(self._h, _ptr(p))
+        return p
+
+
+class RefRMSbank:
+    def __init__(self, N, width=2400, dtype=np.float64):
+        self.dtype, self.N = np.dtype(dtype), N
+        self._h = ref_lib().hgr_rms_create(DTYPES[self.dtype], N, width)
+        if not self._h:
+            raise ValueError("this RMSbank<T,N> is not instantiated in ref_capi.cpp")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().hgr_rms_destroy(self._h)
+            self._h = None
+
+    def process(self, zre, zim=None, calls_per_tick=1):
+        zre = np.ascontiguousarray(zre, dtype=self.dtype)
+        zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
+        out = np.empty_like(zre)
+        ref_lib().hgr_rms_process(self._h, _ptr(zre), _ptr(zim), _ptr(out), zre.shape[1], calls_per_tick)
+        return out

@@ -1,0 +1,89 @@
+"""Golden vectors produced by the reference's own headers (tests/golden/make_golden.py, oracle/_ref):
+the oracle (CPU) and the CUDA path (GPU) must both reproduce them — per-band outputs, phases and RMS
+values bit for bit, the bank sum within the stated tolerance for the GPU (summation order)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TAGS = [("f32", np.float32), ("f64", np.float64)]
+
+
+def same(a, b):
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def _run_fb(cls, g, dtype, **kw):
+    N = int(g["N"])
+    fb = cls(2, N, float(g["k_p"]), float(g["k_g"]), dtype=dtype, fixed=bool(g["fixed"]), **kw)
+    for n in range(N):
+        fb.coefficients(n, g["fwd"][n], g["back"][n])
+    fb.mix(g["gains"])
+    fb.boost(np.ones(N))
+    k = int(g["split"])
+    s1, b1 = fb.process(g["x"][:k], bands=True)
+    fb.boost(3, 0.0)
+    fb.mix(3, 0.0)
+    s2, b2 = fb.process(g["x"][k:], bands=True)
+    return np.concatenate([s1, s2]), np.concatenate([b1, b2], axis=1)
+
+
+def test_golden_files_present():
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) == 8
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+@pytest.mark.parametrize("kind", ["dyn", "fixed"])
+def test_oracle_reproduces_golden_filterbank(oracle_lib, kind, tag, dtype):
+    g = np.load(os.path.join(GOLD, f"filterbank_{kind}_{tag}.npz"))
+    s, b = _run_fb(oracle.Filterbank, g, dtype, mode="strict")
+    assert same(b, g["out_bands"]) and same(s, g["out_sum"])
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_oracle_reproduces_golden_osc_rms(oracle_lib, tag, dtype):
+    g = np.load(os.path.join(GOLD, f"oscbank_{tag}.npz"))
+    osc = oracle.Oscbank(int(g["N"]), dtype=dtype)
+    for i, f in enumerate(g["freqs"]):
+        osc.freqmod(i, f)
+    osc.open()
+    osc.deactivate(g["inactive"])
+    mix = osc.process(len(g["mix"]))
+    assert same(mix.view(dtype), g["mix"].view(dtype)) and same(osc.phases().view(dtype), g["phases_end"].view(dtype))
+    g = np.load(os.path.join(GOLD, f"rmsbank_{tag}.npz"))
+    out = oracle.RMSbank(int(g["N"]), int(g["width"]), dtype=dtype).process(g["zre"], g["zim"])
+    assert same(out, g["out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,dtype", TAGS)
+@pytest.mark.parametrize("kind", ["dyn", "fixed"])
+def test_cuda_reproduces_golden_filterbank(kind, tag, dtype):
+    import huygens_b200 as hb
+    g = np.load(os.path.join(GOLD, f"filterbank_{kind}_{tag}.npz"))
+    s, b = _run_fb(hb.Filterbank, g, dtype, arith="strict")
+    assert same(b, g["out_bands"])
+    assert rel_err(s, g["out_sum"]) <= (1e-5 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_cuda_reproduces_golden_osc_rms(tag, dtype):
+    import huygens_b200 as hb
+    g = np.load(os.path.join(GOLD, f"oscbank_{tag}.npz"))
+    osc = hb.Oscbank(int(g["N"]), dtype=dtype)
+    for i, f in enumerate(g["freqs"]):
+        osc.freqmod(i, f)
+    osc.open()
+    osc.deactivate(g["inactive"])
+    mix = osc.process(len(g["mix"]))
+    assert same(osc.phases().view(dtype), g["phases_end"].view(dtype))
+    assert rel_err(mix.view(dtype), g["mix"].view(dtype)) <= (1e-5 if dtype == np.float32 else 1e-12)
+    g = np.load(os.path.join(GOLD, f"rmsbank_{tag}.npz"))
+    out = hb.RMSbank(int(g["N"]), int(g["width"]), dtype=dtype).process(g["zre"], g["zim"])
+    assert same(out, g["out"])
