@@ -292,15 +292,20 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
     k1_config(fb, &F, &groups);
     fb->last_F = F;
     fb->last_ctas = groups * fb->S;
+    // ws kernel: thread-block clusters reduce the per-CTA partial sums in distributed shared memory
+    int cs = 1;
+    if (F == 0) cs = fb->force_cluster >= 1 ? fb->force_cluster : fb_ws_cluster_size<T>(groups, fb->S);
+    if (cs < 1 || groups % cs) cs = 1;
+    const int rows = groups / cs;            // partial-sum rows that reach HBM
     // segment the block so the partial-sum scratch stays bounded
     size_t seg = L;
-    if (groups > 1 && d_out) {
+    if (rows > 1 && d_out) {
         const size_t budget = (size_t)256 << 20;
-        size_t per_sample = (size_t)groups * fb->S * sizeof(T);
+        size_t per_sample = (size_t)rows * fb->S * sizeof(T);
         size_t max_seg = budget / per_sample;
         max_seg = max_seg < 4096 ? 4096 : (max_seg / 1024) * 1024;
         if (seg > max_seg) seg = max_seg;
-        HG_TRY(fb->partial.reserve((size_t)groups * fb->S * seg * sizeof(T)));
+        HG_TRY(fb->partial.reserve((size_t)rows * fb->S * seg * sizeof(T)));
     }
     const bool vec_ok = d_bands && (((uintptr_t)d_bands) % 16 == 0) && (L % 4 == 0);
     for (size_t t0 = 0; t0 < L; t0 += seg) {
@@ -313,7 +318,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         fb->xh_cur ^= 1;
         P.in = d_in + t0;
         P.in_stride = (long)L;
-        P.direct = (groups == 1) ? 1 : 0;
+        P.direct = (rows == 1) ? 1 : 0;
         P.out = d_out ? (P.direct ? d_out + t0 : (T*)fb->partial.p) : nullptr;
         P.out_stride = (long)L;
         P.bands = d_bands ? d_bands + t0 : nullptr;
@@ -326,14 +331,14 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
-        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, P, groups, st);
+        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, P, groups, st);
         else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);
         fb->last_launches++;
         if (!P.direct && d_out) {
             dim3 grid((unsigned)((len + 255) / 256), fb->S);
-            fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, groups, fb->S, (long)len, (long)L);
+            fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, rows, fb->S, (long)len, (long)L);
             HG_CUDA(cudaGetLastError());
             fb->last_launches++;
         }

@@ -72,6 +72,8 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     if (e) fb->force_F = atoi(e);
     e = getenv("HG_FB_FORCE_CHUNKS");
     if (e) fb->force_chunks = atoi(e);
+    e = getenv("HG_FB_CLUSTER");
+    if (e) fb->force_cluster = atoi(e);
     cudaError_t ce;
     if ((ce = cudaMallocHost(&fb->h_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_par, 7 * N * es)) != cudaSuccess ||

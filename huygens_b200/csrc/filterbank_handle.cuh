@@ -23,6 +23,7 @@ struct hg_fb {
     hg::DevBuf in_stage, out_stage, bands_stage, partial, scan_a, scan_b;
     int force_F = 0;      // HG_FB_FORCE_F: 1,2,4,8 = filters per thread of the lane kernel; -1 = warp-specialised kernel
     int force_chunks = 0;
+    int force_cluster = -1;   // HG_FB_CLUSTER: cluster size of the ws kernel (1 disables), -1 = automatic
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
 };
@@ -49,7 +50,9 @@ template <typename T> struct FbK1Params {
 template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
 template <typename T>
-hg_status fb_launch_exact_ws(bool fma, bool bands, const FbK1Params<T>& P, int groups, cudaStream_t st);
+hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, const FbK1Params<T>& P, int groups, cudaStream_t st);
+template <typename T>
+int fb_ws_cluster_size(int groups, int streams);
 template <typename T>
 hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st);
 

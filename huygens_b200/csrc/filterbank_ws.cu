@@ -26,6 +26,7 @@ namespace ws {
 constexpr int XT = 1024;      // input chunk (samples)
 constexpr int XB = 3;         // input ring depth
 constexpr int NB = 3;         // u / v tile ring depth
+constexpr int CS_MAX = 8;     // thread-block cluster size of the in-cluster partial-sum reduction
 
 template <typename T> struct Cfg;
 template <> struct Cfg<float> { static constexpr int TILE = 128, RS = 132; };    // RS/4 odd: conflict-free 128-bit rows
@@ -68,6 +69,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- thread-block cluster / distributed shared memory helpers -----------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned map_to_cta(const void* local_smem, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void remote_arrive(unsigned remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* b, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void remote_store_row(unsigned raddr, const float (&v)[4]) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void remote_store_row(unsigned raddr, const double (&v)[2]) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(raddr), "d"(v[0]), "d"(v[1]) : "memory");
+}
+
 template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&x)[4]);
 template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&x)[4]) {
     float4 v = *reinterpret_cast<const float4*>(p);
@@ -105,7 +140,9 @@ template <typename T> struct Smem {
     alignas(16) T v[NB][32 * RS];      // R -> S: per-sample mix gains g[t], only while they still move
     T gval[NB][32];                    // converged mix gains of the tile's 32 filters
     int gtile[NB];                     // 1: gains in v (per sample);  0: gains in gval (constant)
+    alignas(16) T cred[2][CS_MAX - 1][TILE];   // cluster leader: partial-sum rows of the other CTAs (via DSMEM)
     unsigned long long x_full[XB], x_empty[XB], u_full[NB], u_empty[NB], v_full[NB], v_empty[NB];
+    unsigned long long c_full[2], c_empty[2];  // cluster-scope hand-over of the cred slots
 };
 
 }  // namespace ws
@@ -170,7 +207,10 @@ __device__ __forceinline__ void ws_u_tile(const T* __restrict__ xc, T* __restric
     }
 }
 
-template <typename T, bool FMA, bool BANDS>
+// CS > 1: the kernel is launched in thread-block clusters of CS CTAs; their S warps push the partial
+// sums of each tile into the leader CTA's shared memory (DSMEM) and the leader writes ONE row per
+// cluster, in fixed CTA order (deterministic).  HBM then sees groups/CS partial rows instead of groups.
+template <typename T, bool FMA, bool BANDS, int CS>
 __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
     using namespace ws;
     typedef Ar<T, FMA> A;
@@ -201,9 +241,14 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
             mbar_init(&sm.u_full[i], 1); mbar_init(&sm.u_empty[i], 1);
             mbar_init(&sm.v_full[i], 1); mbar_init(&sm.v_empty[i], 1);
         }
+        if (CS > 1) {
+            mbar_init(&sm.c_full[0], 32 * (CS - 1)); mbar_init(&sm.c_full[1], 32 * (CS - 1));
+            mbar_init(&sm.c_empty[0], 1); mbar_init(&sm.c_empty[1], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (CS > 1) cluster_sync_all();      // every CTA's barriers exist before anyone arrives remotely
 
     if (role == 3) {
         // ---------------- L: input loader ----------------
@@ -376,8 +421,9 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
         // function of (y, g) whether the gains still move (g tile) or not (gval), so the sum does
         // not depend on how the block is split into calls or tiles.
         T* out_row = nullptr;
-        if (P.out) out_row = P.direct ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
+        if (P.out) out_row = P.direct ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)(grp / CS) * P.S + s) * (size_t)L);
         const bool out_vec = out_row && ((((uintptr_t)out_row) & 15) == 0);
+        const unsigned crank = CS > 1 ? cluster_ctarank() : 0u;
         const int rows = min(32, N - grp * 32);
         int ub = 0;
         unsigned upar = 0;
@@ -412,7 +458,28 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
                     }
                 }
             }
-            if (out_row) {
+            if (CS > 1 && out_row) {
+                const int slot = k & 1;
+                const unsigned use_par = (unsigned)((k >> 1) & 1);
+                if (crank != 0) {
+                    // hand this CTA's row to the leader: wait until it has consumed the slot's last use
+                    mbar_wait_cluster(&sm.c_empty[slot], use_par ^ 1u);
+                    remote_store_row(map_to_cta(&sm.cred[slot][crank - 1][SPL * lane], 0), acc);
+                    remote_arrive(map_to_cta(&sm.c_full[slot], 0));
+                } else {
+                    mbar_wait_cluster(&sm.c_full[slot], use_par);
+#pragma unroll
+                    for (int r = 0; r < CS - 1; r++) {
+                        T rv[SPL];
+                        ldrow<T>(&sm.cred[slot][r][SPL * lane], rv);
+#pragma unroll
+                        for (int j = 0; j < SPL; j++) acc[j] += rv[j];
+                    }
+                    __syncwarp();
+                    if (lane < CS - 1) remote_arrive(map_to_cta(&sm.c_empty[slot], (unsigned)lane + 1u));
+                }
+            }
+            if (out_row && crank == 0) {
                 T* dst = out_row + tg + SPL * lane;
                 if (out_vec && tn == TILE && ((tg * sizeof(T)) & 15) == 0) strow<T>(dst, acc);
                 else {
@@ -425,25 +492,77 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
             if (++ub == NB) { ub = 0; upar ^= 1u; }
         }
     }
+    // no CTA may exit while a peer can still touch its shared memory or barriers
+    if (CS > 1) cluster_sync_all();
 }
 
-template <typename T, bool FMA, bool BANDS>
+template <typename T, bool FMA, bool BANDS, int CS>
 static hg_status launch_ws(const FbK1Params<T>& P, int groups, cudaStream_t st) {
     typedef ws::Smem<T> SM;
     const size_t smem = sizeof(SM);
-    auto kern = fb_exact_ws_kernel<T, FMA, BANDS>;
+    auto kern = fb_exact_ws_kernel<T, FMA, BANDS, CS>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(groups, P.S), 128, smem, st>>>(P);
-    HG_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups, P.S);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    HG_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     return HG_OK;
 }
 
+// largest cluster size (8, 4, 2 or 1) that divides the group count and whose clusters are all
+// co-resident in one wave (each CTA runs the whole block, so a second wave would double the time)
 template <typename T>
-hg_status fb_launch_exact_ws(bool fma, bool bands, const FbK1Params<T>& P, int groups, cudaStream_t st) {
-    if (bands) return fma ? launch_ws<T, true, true>(P, groups, st) : launch_ws<T, false, true>(P, groups, st);
-    return fma ? launch_ws<T, true, false>(P, groups, st) : launch_ws<T, false, false>(P, groups, st);
+int fb_ws_cluster_size(int groups, int streams) {
+    static int cached_groups = -1, cached_streams = -1, cached_cs = 1;
+    if (groups == cached_groups && streams == cached_streams) return cached_cs;
+    int best = 1;
+    for (int cs = ws::CS_MAX; cs > 1; cs >>= 1) {
+        if (groups % cs) continue;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(groups, streams);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = sizeof(ws::Smem<T>);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        const void* fn = cs == 8 ? (const void*)fb_exact_ws_kernel<T, false, false, 8> : cs == 4 ? (const void*)fb_exact_ws_kernel<T, false, false, 4>
+                                                                                        : (const void*)fb_exact_ws_kernel<T, false, false, 2>;
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem<T>));
+        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+        if ((long)nclusters * cs >= (long)groups * streams) { best = cs; break; }
+    }
+    cached_groups = groups; cached_streams = streams; cached_cs = best;
+    return best;
 }
-template hg_status fb_launch_exact_ws<float>(bool, bool, const FbK1Params<float>&, int, cudaStream_t);
-template hg_status fb_launch_exact_ws<double>(bool, bool, const FbK1Params<double>&, int, cudaStream_t);
+template int fb_ws_cluster_size<float>(int, int);
+template int fb_ws_cluster_size<double>(int, int);
+
+template <typename T, bool FMA, bool BANDS>
+static hg_status launch_ws_cs(int cs, const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    switch (cs) {
+        case 8: return launch_ws<T, FMA, BANDS, 8>(P, groups, st);
+        case 4: return launch_ws<T, FMA, BANDS, 4>(P, groups, st);
+        case 2: return launch_ws<T, FMA, BANDS, 2>(P, groups, st);
+    }
+    return launch_ws<T, FMA, BANDS, 1>(P, groups, st);
+}
+
+template <typename T>
+hg_status fb_launch_exact_ws(bool fma, bool bands, int cs, const FbK1Params<T>& P, int groups, cudaStream_t st) {
+    if (bands) return fma ? launch_ws_cs<T, true, true>(cs, P, groups, st) : launch_ws_cs<T, false, true>(cs, P, groups, st);
+    return fma ? launch_ws_cs<T, true, false>(cs, P, groups, st) : launch_ws_cs<T, false, false>(cs, P, groups, st);
+}
+template hg_status fb_launch_exact_ws<float>(bool, bool, int, const FbK1Params<float>&, int, cudaStream_t);
+template hg_status fb_launch_exact_ws<double>(bool, bool, int, const FbK1Params<double>&, int, cudaStream_t);
 
 }  // namespace hg
