@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(128) scan_prepass(ScanParams<T> P) {
 }
 
 // ---- 2. pass 1: zero-state render of every chunk -------------------------------------------------
-template <typename T, bool FMA, int F>
+// TAPS == 2: every filter has b1 == 0 and b2 == -b0 (all reference callers): u = (b0 p)(x[t] - x[t-2])
+template <typename T, bool FMA, int F, int TAPS>
 __global__ void __launch_bounds__(K2_NT) scan_pass1(ScanParams<T> P) {
     typedef Ar<T, FMA> A;
     constexpr int NT = K2_NT, NW = NT / 32, RS = NT + NW;
@@ -159,13 +160,19 @@ __global__ void __launch_bounds__(K2_NT) scan_pass1(ScanParams<T> P) {
 #pragma unroll 4
                 for (int tt = 0; tt < tn; tt++) {
                     const T x0 = xc[tt0 + tt];
+                    const T d = x0 - x2;
                     T acc = (T)0;
 #pragma unroll
                     for (int f = 0; f < F; f++) {
-                        T u = bp2[f] * x2;
-                        u = fma(bp1[f], x1, u);
-                        u = fma(bp0[f], x0, u);
-                        const T t = fma(na2[f], y2[f], u);
+                        T t;
+                        if (TAPS == 2) {
+                            t = fma(na2[f], y2[f], bp0[f] * d);
+                        } else {
+                            T u = bp2[f] * x2;
+                            u = fma(bp1[f], x1, u);
+                            u = fma(bp0[f], x0, u);
+                            t = fma(na2[f], y2[f], u);
+                        }
                         const T y = fma(na1[f], y1[f], t);
                         y2[f] = y1[f]; y1[f] = y;
                         acc = fma(y, g[f], acc);
@@ -376,12 +383,12 @@ __global__ void __launch_bounds__(256) scan_reduce(const T* __restrict__ partial
     out[(size_t)s * L + i] = sum;
 }
 
-template <typename T, bool FMA, int F>
+template <typename T, bool FMA, int F, int TAPS>
 static hg_status scan_launch(hg_fb* fb, ScanParams<T>& P, int groups, T* d_out, cudaStream_t st) {
     constexpr int NW = K2_NT / 32;
     const size_t smem1 = sizeof(T) * (2 * K2_XT + 2 * K2_TILE * (K2_NT + NW));
     const size_t smem2 = sizeof(T) * (2 * K2_TILE * (K2_NT + NW));
-    auto k1 = scan_pass1<T, FMA, F>;
+    auto k1 = scan_pass1<T, FMA, F, TAPS>;
     auto k2 = scan_pass2<T, FMA, F>;
     if (smem1 > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if (smem2 > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -435,8 +442,13 @@ hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStre
     P.N = N; P.S = S; P.C = (int)C; P.L = (long)L; P.Lc = Lc;
     P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
     const bool fma = fb->arith == HG_ARITH_FMA;
-    if (sizeof(T) == 4) return fma ? scan_launch<T, true, 8>(fb, P, groups, d_out, st) : scan_launch<T, false, 8>(fb, P, groups, d_out, st);
-    return fma ? scan_launch<T, true, 4>(fb, P, groups, d_out, st) : scan_launch<T, false, 4>(fb, P, groups, d_out, st);
+    const bool anti = fb->taps == 2;
+    if (sizeof(T) == 4) {
+        if (anti) return fma ? scan_launch<T, true, 8, 2>(fb, P, groups, d_out, st) : scan_launch<T, false, 8, 2>(fb, P, groups, d_out, st);
+        return fma ? scan_launch<T, true, 8, 0>(fb, P, groups, d_out, st) : scan_launch<T, false, 8, 0>(fb, P, groups, d_out, st);
+    }
+    if (anti) return fma ? scan_launch<T, true, 4, 2>(fb, P, groups, d_out, st) : scan_launch<T, false, 4, 2>(fb, P, groups, d_out, st);
+    return fma ? scan_launch<T, true, 4, 0>(fb, P, groups, d_out, st) : scan_launch<T, false, 4, 0>(fb, P, groups, d_out, st);
 }
 
 template hg_status fb_process_scan<float>(hg_fb*, const float*, float*, size_t, cudaStream_t);

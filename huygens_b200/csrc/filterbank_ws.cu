@@ -358,14 +358,19 @@ __global__ void __launch_bounds__(128, 1) fb_exact_ws_kernel(FbK1Params<T> P) {
                 if (lane == 0) sm.gtile[ub] = 0;
                 sm.gval[ub][lane] = g;
                 T t2 = A::mul(a2, y2);
-                T first[4];
-                if (have_u0) { first[0] = u0[0]; first[1] = u0[1]; first[2] = u0[2]; first[3] = u0[3]; }
-                else ld4<T>(urow, first);
+                // rotating register buffers, three groups deep: group q+2 is requested while group q runs,
+                // so a u load has ~96 cycles to land even when the SM's shared-memory pipe is busy
+                // with the U and S warps (measured: one group of look-ahead left ~1 cycle/sample of
+                // short-scoreboard stalls on the chain)
+                T ub3[3][4];
+                if (have_u0) { ub3[0][0] = u0[0]; ub3[0][1] = u0[1]; ub3[0][2] = u0[2]; ub3[0][3] = u0[3]; }
+                else ld4<T>(urow, ub3[0]);
+                ld4<T>(urow + 4, ub3[1]);
 #pragma unroll
                 for (int q = 0; q < TILE / 4; q++) {
-                    T uc[4], yy[4];
-                    if (q == 0) { uc[0] = first[0]; uc[1] = first[1]; uc[2] = first[2]; uc[3] = first[3]; }
-                    else ld4<T>(urow + 4 * q, uc);               // hoisted by the scheduler into the chain's stall slots
+                    T yy[4];
+                    if (q + 2 < TILE / 4) ld4<T>(urow + 4 * (q + 2), ub3[(q + 2) % 3]);
+                    const T(&uc)[4] = ub3[q % 3];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         // filterbank.h:179 fb = fl(fl(a1 y1) + fl(a2 y2)); :178-179 y = fl(u - fb)

@@ -91,8 +91,13 @@ __device__ __forceinline__ void cta_tile_reduce(const T* rb, int tn, T* out, int
     const T* row = rb + t * RS + jq;
     T sum = (T)0;
     if (t < tn) {
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) sum += row[i * NW];
+        // four independent partial sums keep the dependent-add chain 8 deep instead of 32
+        T s0 = (T)0, s1 = (T)0, s2 = (T)0, s3 = (T)0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            s0 += row[(i + 0) * NW]; s1 += row[(i + 1) * NW]; s2 += row[(i + 2) * NW]; s3 += row[(i + 3) * NW];
+        }
+        sum = (s0 + s1) + (s2 + s3);
     }
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
