@@ -51,9 +51,21 @@ template <typename T, int F> struct Lane {
     T y1[F], y2[F], p[F], g[F], cp[F], cg[F];
 };
 
-// one sample for the F filters of this thread; returns sum_f y_f * g_f
+// tests/filterbank.cpp:158-171 softclip(sample, width = 0.125), evaluated in double like the
+// reference's `double softclip(double)` and rounded to T.  Device atan is within 2 ulp of the
+// correctly rounded value (CUDA math API), so this path is tolerance-bounded, not bit-exact.
+template <typename T> __device__ __forceinline__ T softclip_dev(T v) {
+    const double PI_REF = 3.14159265359, width = 0.125;       // src/includes.h:30
+    const double sample = (double)v;
+    if (fabs(sample) < width) return v;
+    const double sign = (0.0 < sample) - (sample < 0.0);
+    const double gap = sample - sign * width;
+    return (T)(sign * width + (1 - width) * 2.0 / PI_REF * atan(PI_REF * gap / (2 * (1 - width))));
+}
+
+// one sample for the F filters of this thread; returns sum_f y_f * g_f (or sum_f softclip(y_f * g_f))
 template <typename T, bool FMA, int F, bool SMOOTH, bool BANDS>
-__device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T s_g, T (&yb)[F]) {
+__device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T s_g, T (&yb)[F], int dist = 0) {
     typedef Ar<T, FMA> A;
     T acc = (T)0;
 #pragma unroll
@@ -71,7 +83,8 @@ __device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T
         r.y2[f] = r.y1[f];
         r.y1[f] = y;
         if (BANDS) yb[f] = y;
-        acc = A::acc(y, r.g[f], acc);                    // :130  row . gains_out
+        if (dist) acc = A::add(acc, softclip_dev<T>(A::mul(y, r.g[f])));   // :133-139  sum_n distortion(y_n g_n)
+        else acc = A::acc(y, r.g[f], acc);               // :130  row . gains_out
     }
     return acc;
 }
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                     lds4<T>(xc + t0 + tt, xv);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        T acc = k1_sample<T, FMA, F, false, BANDS>(r, xv[k], x1, x2, P.s_p, P.s_g, ybs);
+                        T acc = k1_sample<T, FMA, F, false, BANDS>(r, xv[k], x1, x2, P.s_p, P.s_g, ybs, P.dist);
                         x2 = x1; x1 = xv[k];
                         rb[(tt + k) * RS + tid] = acc;
                         if (BANDS) {
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                 }
                 for (; tt < tn; tt++) {
                     const T x0 = xc[t0 + tt];
-                    T acc = k1_sample<T, FMA, F, false, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs);
+                    T acc = k1_sample<T, FMA, F, false, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
                     x2 = x1; x1 = x0;
                     rb[tt * RS + tid] = acc;
                     if (BANDS) {
@@ -191,7 +204,7 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
             } else {
                 for (; tt < tn; tt++) {
                     const T x0 = xc[t0 + tt];
-                    T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs);
+                    T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
                     x2 = x1; x1 = x0;
                     rb[tt * RS + tid] = acc;
                     if (BANDS) {
@@ -271,12 +284,13 @@ static void k1_config(const hg_fb* fb, int* F_out, int* groups_out) {
     int F = 1;
     // latency-bound regime (every CTA of 32 filters resident at once, one per SM): the
     // warp-specialised kernel, reported as F = 0
-    if (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 32)) {
+    if (!fb->cur_dist && (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 32))) {
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
         return;
     }
     if (fb->force_F > 0) F = fb->force_F;
+    else if (fb->force_F < 0 && fb->cur_dist) F = 1;
     else if (lanes >= smsp_threads * 8 * 2) F = 8;
     else if (lanes >= smsp_threads * 4) F = 4;
     else if (lanes >= smsp_threads * 2) F = 2;
@@ -325,6 +339,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.bands_stride = (long)L;
         P.bands_vec = (vec_ok && (t0 % 4 == 0)) ? 1 : 0;
         P.taps = fb->taps;
+        P.dist = fb->cur_dist;
         P.N = fb->N;
         P.S = fb->S;
         P.L = (long)len;

@@ -152,8 +152,11 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null handle");
     if (mode != HG_MODE_AUTO && mode != HG_MODE_EXACT && mode != HG_MODE_SCAN)
         return hg::fail(HG_ERR_INVALID, "hg_fb_process: bad mode %d", mode);
-    if (distortion != HG_DIST_NONE)
-        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: distortion %d not built yet", distortion);
+    if (distortion != HG_DIST_NONE && distortion != HG_DIST_SOFTCLIP)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_process: bad distortion %d", distortion);
+    if (distortion != HG_DIST_NONE && mode == HG_MODE_SCAN)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: a per-band nonlinearity needs the exact mode");
+    fb->cur_dist = distortion;
     fb->last_launches = 0;
     if (L == 0) return HG_OK;
     if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
@@ -200,6 +203,7 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     }
 
     int use = mode;
+    if (distortion != HG_DIST_NONE) use = HG_MODE_EXACT;
     if (use == HG_MODE_AUTO) {
         // scan only pays when the lanes cannot fill the schedulers and the block is long; it is
         // not bit-identical, so AUTO keeps fp32 on the exact path.

@@ -20,6 +20,7 @@ struct hg_fb {
     void* d_state = nullptr;
     void* d_xh = nullptr;
     int xh_cur = 0;
+    int cur_dist = 0;            // distortion of the block being processed
     hg::DevBuf in_stage, out_stage, bands_stage, partial, scan_a, scan_b;
     int force_F = 0;      // HG_FB_FORCE_F: 1,2,4,8 = filters per thread of the lane kernel; -1 = warp-specialised kernel
     int force_chunks = 0;
@@ -44,6 +45,7 @@ template <typename T> struct FbK1Params {
     T c_p, s_p, c_g, s_g;
     int direct;
     int bands_vec;
+    int dist;      // HG_DIST_*: per-band nonlinearity before the sum (lane kernel only)
     int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
 };
 
