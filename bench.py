@@ -35,6 +35,9 @@ WORKLOADS = {
     "c2": dict(N=4096, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
     # BASELINE configs[2] (65,536 filters; a parity/scaling case, not the headline): 10 s blocks
     "c3": dict(N=65536, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
+    # the per-GPU shards of configs[2] at 8 and 4 GPUs
+    "c3_8192": dict(N=8192, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
+    "c3_16384": dict(N=16384, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
 }
 
 

@@ -278,13 +278,19 @@ static hg_status launch_k1_F(int F, const FbK1Params<T>& P, int groups, cudaStre
 
 // choose filters-per-thread so that the grid covers the SMs; more filters per thread amortise the
 // per-sample reduction overhead, fewer expose more lanes.
-static void k1_config(const hg_fb* fb, int* F_out, int* groups_out) {
+static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     const long lanes = (long)fb->N * fb->S;
     const long smsp_threads = (long)fb->sm_count * 4 * 32;   // one warp per scheduler
     int F = 1;
-    // latency-bound regime (every CTA of 32 filters resident at once, one per SM): the
-    // warp-specialised kernel, reported as F = 0
-    if (!fb->cur_dist && (fb->force_F < 0 || (fb->force_F == 0 && lanes <= (long)fb->sm_count * 32))) {
+    // latency-bound regime: every CTA of 32 filters resident at once, 1, 2 or 4 per SM (fp64: 1 or 2)
+    // -> the warp-specialised kernel, reported as F = 0
+    const long ws_ctas = (long)((fb->N + 31) / 32) * fb->S;
+    const int max_level = fb->dtype == HG_F32 ? 2 : 1;
+    int level = 0;
+    while (level < max_level && ws_ctas > ((long)fb->sm_count << level)) level++;
+    const bool ws_fits = ws_ctas <= ((long)fb->sm_count << level);
+    if (!fb->cur_dist && (fb->force_F < 0 || (fb->force_F == 0 && ws_fits))) {
+        fb->ws_level = level;
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
         return;
@@ -308,7 +314,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
     fb->last_ctas = groups * fb->S;
     // ws kernel: thread-block clusters reduce the per-CTA partial sums in distributed shared memory
     int cs = 1;
-    if (F == 0) cs = fb->force_cluster >= 1 ? fb->force_cluster : fb_ws_cluster_size<T>(groups, fb->S);
+    if (F == 0) cs = fb->force_cluster >= 1 ? fb->force_cluster : fb_ws_cluster_size<T>(groups, fb->S, fb->ws_level);
     if (cs < 1 || groups % cs) cs = 1;
     const int rows = groups / cs;            // partial-sum rows that reach HBM
     // segment the block so the partial-sum scratch stays bounded
@@ -346,7 +352,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
-        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, P, groups, st);
+        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
         else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);

@@ -27,6 +27,7 @@ struct hg_fb {
     int force_cluster = -1;   // HG_FB_CLUSTER: cluster size of the ws kernel (1 disables), -1 = automatic
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
+    int ws_level = 0;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
 };
 
 namespace hg {
@@ -52,9 +53,9 @@ template <typename T> struct FbK1Params {
 template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
 template <typename T>
-hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, const FbK1Params<T>& P, int groups, cudaStream_t st);
+hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, int level, const FbK1Params<T>& P, int groups, cudaStream_t st);
 template <typename T>
-int fb_ws_cluster_size(int groups, int streams);
+int fb_ws_cluster_size(int groups, int streams, int level);
 template <typename T>
 hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st);
 
