@@ -313,6 +313,14 @@ def main():
     per_gpu_kernel = float(N) * L * args.steps / t_kernel
     achieved = per_gpu_kernel * SLOTS_PER_FILTER_SAMPLE
     nominal = peak["sm_count"] * 128 * 1.965e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.mode == "exact" and args.workload == "c2":
+            traffic = {"dram_bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "samples_per_launch": tr["samples_per_launch"],
+                       "algorithmic_bytes_per_launch": 8 * tr["samples_per_launch"], "source": tr["source"], "note": tr["note"]}
+    except Exception:
+        pass
     line = {
         "metric": "filter-samples/s (biquad bank)", "value": value, "unit": "filter-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
@@ -322,7 +330,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
-                     "frac": achieved / peak["slots_per_s"], "traffic": None,
+                     "frac": achieved / peak["slots_per_s"], "traffic": traffic,
                      "peak_source": "hg_fma_peak FFMA microbenchmark, measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                      "frac_of_nominal": achieved / nominal, "slots_per_unit": SLOTS_PER_FILTER_SAMPLE,
                      "kernel_ms": t_kernel / args.steps * 1e3, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],

@@ -24,6 +24,7 @@
 // few hundred Hz at r = 0.999 and fails below).
 #include <cuda_pipeline.h>
 #include <cmath>
+#include <cstdlib>
 #include "hg_common.cuh"
 #include "filterbank_handle.cuh"
 
@@ -410,7 +411,8 @@ template <typename T>
 hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st) {
     if (!d_out) return fail(HG_ERR_INVALID, "scan mode needs out_sum");
     const int N = fb->N, S = fb->S;
-    const int F = (sizeof(T) == 4) ? 8 : 4;
+    int F = (sizeof(T) == 4) ? 8 : 4;
+    if (const char* e = getenv("HG_SCAN_F")) { if (atoi(e) == 4) F = 4; if (atoi(e) == 8 && sizeof(T) == 4) F = 8; }
     // enough lanes for ~2 warps per scheduler; chunks are multiples of the input staging size
     const long want_threads = (long)fb->sm_count * 4 * 32 * 2;
     long C = (want_threads * F + (long)S * N - 1) / ((long)S * N);
@@ -443,7 +445,7 @@ hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStre
     P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
     const bool fma = fb->arith == HG_ARITH_FMA;
     const bool anti = fb->taps == 2;
-    if (sizeof(T) == 4) {
+    if (F == 8) {
         if (anti) return fma ? scan_launch<T, true, 8, 2>(fb, P, groups, d_out, st) : scan_launch<T, false, 8, 2>(fb, P, groups, d_out, st);
         return fma ? scan_launch<T, true, 8, 0>(fb, P, groups, d_out, st) : scan_launch<T, false, 8, 0>(fb, P, groups, d_out, st);
     }
