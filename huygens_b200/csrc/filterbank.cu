@@ -289,10 +289,17 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     int level = 0;
     while (level < max_level && ws_ctas > ((long)fb->sm_count << level)) level++;
     const bool ws_fits = ws_ctas <= ((long)fb->sm_count << level);
-    if (!fb->cur_dist && (fb->force_F < 0 || (fb->force_F == 0 && ws_fits))) {
+    if (!fb->cur_dist && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
         fb->ws_level = level;
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
+        return;
+    }
+    // throughput regime: the RU/S kernel (reported as F = -2); the lane kernel below stays for the
+    // per-band nonlinearity and as a forced alternative (HG_FB_FORCE_F > 0)
+    if (!fb->cur_dist && (fb->force_F == 0 || fb->force_F == -2)) {
+        *F_out = -2;
+        *groups_out = 0;
         return;
     }
     if (fb->force_F > 0) F = fb->force_F;
@@ -310,8 +317,13 @@ template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st) {
     int F, groups;
     k1_config(fb, &F, &groups);
+    int ru_W = 0, ru_cps = 0;
+    if (F == -2) {
+        fb_ru_config<T>(fb, &ru_W, &ru_cps);
+        groups = ru_cps;                     // partial-sum rows per stream: one per CTA
+    }
     fb->last_F = F;
-    fb->last_ctas = groups * fb->S;
+    fb->last_ctas = (F == -2 ? ru_cps : groups) * fb->S;
     // ws kernel: thread-block clusters reduce the per-CTA partial sums in distributed shared memory
     int cs = 1;
     if (F == 0) cs = fb->force_cluster >= 1 ? fb->force_cluster : fb_ws_cluster_size<T>(groups, fb->S, fb->ws_level);
@@ -353,6 +365,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
         if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
+        else if (F == -2) rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st);
         else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);

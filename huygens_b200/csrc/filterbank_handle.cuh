@@ -57,6 +57,10 @@ hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, int level, const
 template <typename T>
 int fb_ws_cluster_size(int groups, int streams, int level);
 template <typename T>
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st);
+template <typename T>
+void fb_ru_config(const hg_fb* fb, int* W_out, int* ctas_per_stream_out);
+template <typename T>
 hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st);
 
 }  // namespace hg

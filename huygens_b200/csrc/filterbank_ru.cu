@@ -1,0 +1,445 @@
+// filterbank_ru.cu — K1-ru: exact Filterbank kernel for the throughput regime (more lanes than the
+// warp-specialised kernel can keep resident: BASELINE configs[2] on one GPU, configs[3]).
+//
+// Same bit-exact arithmetic as filterbank_ws.inc (reference: src/filterbank.h:170-187), different
+// division of labour: with many warps per scheduler the 12-cycle dependency chain of one lane hides
+// behind the other warps, so the goal is the lowest instruction count per filter-sample, not the
+// shortest critical path.
+//     RU warps  lane = filter: feed-forward taps, pre-gain and the recurrence (x by LDS.128 broadcast,
+//               y out by STS.128 into a 2-deep ring of [32][TILE] tiles); own y1, y2 and p
+//     S warps   lane = sample: out[t] = sum over their RU warps (ascending) and the 32 lanes (ascending)
+//               of fma(y, g, .); own the mix gains g (replayed per sample while they still move) and
+//               stream per-band rows; S warp 0 also feeds the input ring by TMA bulk copies
+// One CTA = W RU warps + 2 S warps of one stream; full/empty mbarriers per RU warp, no __syncthreads in
+// the steady state.  7.5 (taps {g,0,-g}) to 10.5 (general taps) RU instructions + ~3 S instructions
+// per filter-sample against 11 algorithmic issue slots.
+#include "hg_common.cuh"
+#include "filterbank_handle.cuh"
+
+namespace hg {
+
+namespace ru {
+
+constexpr int TILE = 32;      // samples per hand-over tile (S lane = sample)
+constexpr int NB = 2;         // tile ring depth per RU warp
+constexpr int XT = 1024;      // input chunk
+constexpr int XB = 2;         // input ring depth
+constexpr int W_MAX = 14;     // RU warps per CTA
+constexpr int NS = 7;         // S warps per CTA (each serves at most 2 RU warps: an S warp must not need more than its
+                              // fair share of its scheduler's issue slots, or the RU warps starve behind it)
+constexpr int GPS = (W_MAX + NS - 1) / NS;   // RU warps served by one S warp, at most
+
+template <typename T> struct RowStride;      // RS*sizeof(T)/16 odd: conflict-free 128-bit rows
+template <> struct RowStride<float> { static constexpr int RS = TILE + 4; };
+template <> struct RowStride<double> { static constexpr int RS = TILE + 2; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&x)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&x)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<double>(const double* p, double (&x)[4]) {
+    double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const T (&x)[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float (&x)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+template <> __device__ __forceinline__ void st4<double>(double* p, const double (&x)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(x[0], x[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(x[2], x[3]);
+}
+
+// dynamic shared memory layout (W known at launch):
+//   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[2][NS][32] | barriers
+template <typename T> struct Layout {
+    static constexpr int RS = RowStride<T>::RS;
+    int W;
+    __host__ __device__ explicit Layout(int w) : W(w) {}
+    __host__ __device__ size_t xs_off() const { return 0; }
+    __host__ __device__ size_t y_off() const { return sizeof(T) * XB * XT; }
+    __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NB * 32 * RS; }
+    __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * NS * 32 * RS; }
+    __host__ __device__ size_t ps_off() const { return gs_off() + sizeof(T) * NS * GPS * 32; }
+    __host__ __device__ size_t bar_off() const { return (ps_off() + sizeof(T) * 2 * NS * 32 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB); }
+};
+
+}  // namespace ru
+
+template <typename T> struct FbRuParams {
+    FbK1Params<T> k;
+    int W;            // RU warps per CTA
+    int cps;          // CTAs per stream = ceil(ceil(N/32) / W)
+};
+
+template <typename T, bool FMA, bool BANDS>
+__global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kernel(FbRuParams<T> Q) {
+    using namespace ru;
+    typedef Ar<T, FMA> A;
+    constexpr int RS = RowStride<T>::RS;
+    const FbK1Params<T>& P = Q.k;
+    const int W = Q.W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Layout<T> lay(W);
+    T* xs = reinterpret_cast<T*>(smem_raw + lay.xs_off());
+    T* ytiles = reinterpret_cast<T*>(smem_raw + lay.y_off());
+    T* gtiles = reinterpret_cast<T*>(smem_raw + lay.gt_off());
+    T* gsmem = reinterpret_cast<T*>(smem_raw + lay.gs_off());
+    T* psum = reinterpret_cast<T*>(smem_raw + lay.ps_off());
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + lay.bar_off());
+    unsigned long long* x_full = bars;                      // [XB]
+    unsigned long long* x_empty = bars + XB;                // [XB]
+    unsigned long long* y_full = bars + 2 * XB;             // [W][NB]
+    unsigned long long* y_empty = bars + 2 * XB + W * NB;   // [W][NB]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cta = blockIdx.x, s = blockIdx.y;
+    const int N = P.N;
+    const long L = P.L;
+    const int groups = (N + 31) / 32;                       // RU warps of the whole stream
+    const int w_first = cta * W;                            // first filter group of this CTA
+    const int w_here = min(W, groups - w_first);            // RU warps with work
+    const size_t SN = (size_t)P.S * N;
+    const int ntiles = (int)((L + TILE - 1) / TILE);
+    const int nchunks = (int)((L + XT - 1) / XT);
+    const int last_tn = (int)(L - (long)(ntiles - 1) * TILE);
+    constexpr int TPC = XT / TILE;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XB; i++) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], w_here); }
+        for (int i = 0; i < W * NB; i++) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < W) {
+        // ------------------------------ RU: taps, pre-gain, recurrence ------------------------------
+        if (warp >= w_here) return;
+        const int n = (w_first + warp) * 32 + lane;
+        const bool ok = n < N;
+        const size_t si = (size_t)s * N + n;
+        const T b0 = ok ? P.par[0 * (size_t)N + n] : (T)0, b1 = ok ? P.par[1 * (size_t)N + n] : (T)0;
+        const T b2 = ok ? P.par[2 * (size_t)N + n] : (T)0;
+        const T a1 = ok ? P.par[3 * (size_t)N + n] : (T)0, a2 = ok ? P.par[4 * (size_t)N + n] : (T)0;
+        const T pin = ok ? P.par[5 * (size_t)N + n] : (T)0;
+        T y1 = ok ? P.state[0 * SN + si] : (T)0, y2 = ok ? P.state[1 * SN + si] : (T)0;
+        T p = ok ? P.state[2 * SN + si] : (T)0;
+        const T cp = A::mul(P.c_p, pin), s_p = P.s_p;
+        T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
+        T m1 = A::mul(b0, x1), m2 = A::mul(b0, x2);         // taps == 2: fl(b0 x[t-1]), fl(b0 x[t-2])
+        const int taps = FMA ? 0 : P.taps;
+        bool conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+        T* ybase = ytiles + (size_t)warp * NB * 32 * RS + lane * RS;
+        unsigned long long* yf = y_full + warp * NB;
+        unsigned long long* ye = y_empty + warp * NB;
+        int xb = 0, yb = 0, kc = 0;
+        unsigned xpar = 0, ypar = 0;
+        T t2 = A::mul(a2, y2);
+        for (int k = 0; k < ntiles; k++) {
+            if (kc == 0) mbar_wait(&x_full[xb], xpar);
+            mbar_wait(&ye[yb], ypar ^ 1u);
+            const T* xc = xs + xb * XT + kc * TILE;
+            T* yrow = ybase + yb * 32 * RS;
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
+            int tt = 0;
+            if (conv && tn == TILE) {
+                // whole tile unrolled; the next group's inputs are requested before this group is computed
+                T xq[2][4];
+                ld4<T>(xc, xq[0]);
+#pragma unroll
+                for (int q = 0; q < TILE / 4; q++) {
+                    if (q + 1 < TILE / 4) ld4<T>(xc + 4 * (q + 1), xq[(q + 1) & 1]);
+                    const T(&xv)[4] = xq[q & 1];
+                    T yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const T x0 = xv[j];
+                        T fw;
+                        if (taps == 2) {                    // b1 == 0, b2 == -b0: exact identities skipped
+                            const T m0 = A::mul(b0, x0);
+                            fw = A::sub(m0, m2);
+                            m2 = m1; m1 = m0;
+                        } else {
+                            fw = A::mul(b0, x0);                                   // filterbank.h:178
+                            if (taps == 0) fw = A::muladd(b1, x1, fw);
+                            fw = A::muladd(b2, x2, fw);
+                        }
+                        T y;
+                        if (FMA) {
+                            const T fb = A::muladd(a2, y2, A::mul(a1, y1));
+                            y = A::mulsub(fw, p, fb);
+                        } else {
+                            const T u = A::mul(fw, p);
+                            const T fb = A::add(A::mul(a1, y1), t2);              // filterbank.h:179
+                            y = A::sub(u, fb);
+                            t2 = A::mul(a2, y1);
+                        }
+                        y2 = y1; y1 = y;
+                        x2 = x1; x1 = x0;
+                        yy[j] = y;
+                    }
+                    st4<T>(yrow + 4 * q, yy);
+                }
+                tt = TILE;
+            } else if (conv) {
+                for (; tt + 4 <= tn; tt += 4) {
+                    T xv[4];
+                    ld4<T>(xc + tt, xv);
+                    T yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const T x0 = xv[j];
+                        T fw;
+                        if (taps == 2) {                    // b1 == 0, b2 == -b0: exact identities skipped
+                            const T m0 = A::mul(b0, x0);
+                            fw = A::sub(m0, m2);
+                            m2 = m1; m1 = m0;
+                        } else {
+                            fw = A::mul(b0, x0);                                   // filterbank.h:178
+                            if (taps == 0) fw = A::muladd(b1, x1, fw);
+                            fw = A::muladd(b2, x2, fw);
+                        }
+                        T y;
+                        if (FMA) {
+                            const T fb = A::muladd(a2, y2, A::mul(a1, y1));
+                            y = A::mulsub(fw, p, fb);
+                        } else {
+                            const T u = A::mul(fw, p);
+                            const T fb = A::add(A::mul(a1, y1), t2);              // filterbank.h:179
+                            y = A::sub(u, fb);
+                            t2 = A::mul(a2, y1);
+                        }
+                        y2 = y1; y1 = y;
+                        x2 = x1; x1 = x0;
+                        yy[j] = y;
+                    }
+                    st4<T>(yrow + tt, yy);
+                }
+            }
+            for (; tt < tn; tt++) {
+                if (!conv) p = A::muladd(s_p, p, cp);                              // filterbank.h:172
+                const T x0 = xc[tt];
+                T fw = A::mul(b0, x0);
+                fw = A::muladd(b1, x1, fw);
+                fw = A::muladd(b2, x2, fw);
+                T fb = A::mul(a1, y1);
+                fb = A::muladd(a2, y2, fb);
+                const T y = A::mulsub(fw, p, fb);
+                y2 = y1; y1 = y;
+                x2 = x1; x1 = x0;
+                yrow[tt] = y;
+            }
+            if (!conv || (tn & 3)) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
+            if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            __syncwarp();
+            const bool chunk_done = (kc == TPC - 1) || (k == ntiles - 1);
+            if (lane == 0) {
+                mbar_arrive(&yf[yb]);
+                if (chunk_done) mbar_arrive(&x_empty[xb]);
+            }
+            if (++yb == NB) { yb = 0; ypar ^= 1u; }
+            if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
+        }
+        if (ok) { P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[2 * SN + si] = p; }
+        if (cta == 0 && warp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+    } else {
+        // ------------------------------ S: mixdown, gains, input ring ------------------------------
+        const int sidx = warp - W;                          // 0 .. NS-1
+        if (sidx >= NS) return;
+        // RU warps served by this S warp: an even split of the CTA's active RU warps
+        const int per = (w_here + NS - 1) / NS;
+        const int wa = min(w_here, sidx * per), wb = min(w_here, wa + per);
+        const bool feeds = sidx == 0;
+        T* gt = gtiles + (size_t)sidx * 32 * RS;
+        T* gs = gsmem + (size_t)sidx * GPS * 32;            // converged gains, [served RU warp][filter]
+        // lane l holds g, cg of filter l of every served RU warp
+        T g[GPS], cg[GPS];
+        bool gconv = true;
+#pragma unroll
+        for (int i = 0; i < GPS; i++) {
+            const int w = wa + i;
+            const int n = (w_first + w) * 32 + lane;
+            const bool ok = w < wb && n < N;
+            g[i] = ok ? P.state[3 * SN + (size_t)s * N + n] : (T)0;
+            cg[i] = A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0);
+            gconv = gconv && (A::muladd(P.s_g, g[i], cg[i]) == g[i]);
+            gs[i * 32 + lane] = g[i];
+        }
+        gconv = __all_sync(0xffffffffu, gconv);
+        __syncwarp();
+        const T* inp = P.in + (size_t)s * P.in_stride;
+        T* out_row = P.out ? P.out + ((size_t)cta * P.S + s) * (size_t)L : nullptr;     // one partial row per CTA
+        int xb = 0, yb = 0, kc = 0;
+        unsigned xpar = 0, ypar = 0;
+        int next_chunk = 0;
+        for (int k = 0; k < ntiles; k++) {
+            if (feeds) {
+                // keep the input ring full: chunk c may be issued once its slot was released
+                while (next_chunk < nchunks && next_chunk < (k / TPC) + XB) {
+                    const int c = next_chunk, b = c % XB;
+                    mbar_wait(&x_empty[b], (unsigned)(((c / XB) & 1) ^ 1));
+                    const long base = (long)c * XT;
+                    const int cnt = (int)min((long)XT, L - base);
+                    const T* src = inp + base;
+                    const unsigned bytes = (unsigned)(cnt * sizeof(T));
+                    if ((((uintptr_t)src) & 15) == 0 && (bytes & 15) == 0) {
+                        if (lane == 0) { mbar_arrive_tx(&x_full[b], bytes); bulk_g2s(xs + b * XT, src, bytes, &x_full[b]); }
+                    } else {
+                        for (int i = lane; i < cnt; i += 32) xs[b * XT + i] = src[i];
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&x_full[b]);
+                    }
+                    next_chunk++;
+                }
+            }
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
+            const long tg = (long)k * TILE;
+            T acc = (T)0;
+            bool still = false;
+#pragma unroll 1
+            for (int w = wa; w < wb; w++) {
+                const int i = w - wa;
+                mbar_wait(&y_full[w * NB + yb], ypar);
+                const T* yt = ytiles + ((size_t)w * NB + yb) * 32 * RS + lane;
+                // out[t] += sum_l fma(y_l[t], g_l[t], .): four interleaved partial sums over l (ascending),
+                // combined pairwise — the same fixed order whether the gains still move or not
+                T a0 = (T)0, a1s = (T)0, a2s = (T)0, a3 = (T)0;
+                if (!gconv) {
+                    T gi = (T)0, cgi = (T)0;
+#pragma unroll
+                    for (int j = 0; j < GPS; j++) if (j == i) { gi = g[j]; cgi = cg[j]; }
+                    // replay the gain smoother of filter `lane` over the tile (filterbank.h:173) into gt[l][t]
+                    for (int t = 0; t < tn; t++) { gi = A::muladd(P.s_g, gi, cgi); gt[lane * RS + t] = gi; }
+                    still = still || (A::muladd(P.s_g, gi, cgi) != gi);
+#pragma unroll
+                    for (int j = 0; j < GPS; j++) if (j == i) g[j] = gi;
+                    gs[i * 32 + lane] = gi;
+                    __syncwarp();
+#pragma unroll
+                    for (int l = 0; l < 32; l += 4) {
+                        a0 = A::acc(yt[(l + 0) * RS], gt[(l + 0) * RS + lane], a0);                     // filterbank.h:130
+                        a1s = A::acc(yt[(l + 1) * RS], gt[(l + 1) * RS + lane], a1s);
+                        a2s = A::acc(yt[(l + 2) * RS], gt[(l + 2) * RS + lane], a2s);
+                        a3 = A::acc(yt[(l + 3) * RS], gt[(l + 3) * RS + lane], a3);
+                    }
+                    __syncwarp();
+                } else {
+                    const T* gw = gs + i * 32;
+#pragma unroll
+                    for (int l = 0; l < 32; l += 4) {
+                        a0 = A::acc(yt[(l + 0) * RS], gw[l + 0], a0);
+                        a1s = A::acc(yt[(l + 1) * RS], gw[l + 1], a1s);
+                        a2s = A::acc(yt[(l + 2) * RS], gw[l + 2], a2s);
+                        a3 = A::acc(yt[(l + 3) * RS], gw[l + 3], a3);
+                    }
+                }
+                acc += (a0 + a1s) + (a2s + a3);
+                if (BANDS) {
+                    const int rows = min(32, N - (w_first + w) * 32);
+                    for (int l = 0; l < rows; l++)
+                        if (lane < tn) P.bands[((size_t)s * N + (w_first + w) * 32 + l) * P.bands_stride + tg + lane] = yt[l * RS];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&y_empty[w * NB + yb]);
+            }
+            if (!gconv) gconv = !__any_sync(0xffffffffu, still);
+            if (out_row) {
+                // combine the S warps' partial sums in fixed order; one named barrier per tile (the
+                // psum buffers alternate, so the next write to this buffer is two barriers away)
+                T* ps = psum + (size_t)(k & 1) * NS * 32;
+                ps[sidx * 32 + lane] = acc;
+                asm volatile("bar.sync 1, %0;" ::"n"(NS * 32) : "memory");
+                if (sidx == 0 && lane < tn) {
+                    T tot = ps[lane];
+#pragma unroll
+                    for (int i = 1; i < NS; i++) tot += ps[i * 32 + lane];
+                    out_row[tg + lane] = tot;
+                }
+            }
+            if (++yb == NB) { yb = 0; ypar ^= 1u; }
+            if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
+        }
+#pragma unroll
+        for (int i = 0; i < GPS; i++) {
+            const int w = wa + i;
+            const int n = (w_first + w) * 32 + lane;
+            if (w < wb && n < N) P.state[3 * SN + (size_t)s * N + n] = g[i];
+        }
+    }
+}
+
+// pick RU warps per CTA (and 1 or 2 CTAs per SM, as shared memory allows) so that the CTAs fill whole
+// waves: each CTA runs the whole block, so a nearly empty last wave costs a full pass
+template <typename T>
+void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
+    const int groups = (fb->N + 31) / 32;
+    const size_t smem_sm = (size_t)227 * 1024;
+    int bestW = 4;
+    double best = -1;
+    for (int per_sm = 1; per_sm <= 2; per_sm++) {
+        for (int W = 4; W <= ru::W_MAX; W++) {
+            if ((ru::Layout<T>(W).bytes() + 1024) * per_sm > smem_sm) continue;
+            const long slots = (long)fb->sm_count * per_sm;
+            const long ctas = (long)((groups + W - 1) / W) * fb->S;
+            const long waves = (ctas + slots - 1) / slots;
+            // useful RU warp-passes over the warp slots of the waves that run, weighted by how many
+            // RU warps an SM keeps busy (latency hiding needs >= ~3 per scheduler)
+            const double fill = (double)groups * fb->S / ((double)waves * slots * W);
+            const double busy = (double)(W * per_sm) / 16.0;
+            const double eff = fill * (busy > 1.0 ? 1.0 : busy);
+            if (eff > best + 1e-9) { best = eff; bestW = W; }
+        }
+    }
+    *W_out = bestW;
+    *cps_out = (groups + bestW - 1) / bestW;
+}
+template void fb_ru_config<float>(const hg_fb*, int*, int*);
+template void fb_ru_config<double>(const hg_fb*, int*, int*);
+
+template <typename T, bool FMA, bool BANDS>
+static hg_status launch_ru(const FbK1Params<T>& P, int W, int cps, cudaStream_t st) {
+    FbRuParams<T> Q;
+    Q.k = P; Q.W = W; Q.cps = cps;
+    const size_t smem = ru::Layout<T>(W).bytes();
+    auto kern = fb_exact_ru_kernel<T, FMA, BANDS>;
+    HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(cps, P.S), (W + ru::NS) * 32, smem, st>>>(Q);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}
+
+template <typename T>
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int cps, cudaStream_t st) {
+    if (bands) return fma ? launch_ru<T, true, true>(P, W, cps, st) : launch_ru<T, false, true>(P, W, cps, st);
+    return fma ? launch_ru<T, true, false>(P, W, cps, st) : launch_ru<T, false, false>(P, W, cps, st);
+}
+template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, cudaStream_t);
+template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, cudaStream_t);
+
+}  // namespace hg
