@@ -87,10 +87,57 @@ template <typename T> struct Layout {
     __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * NS * 32 * RS; }
     __host__ __device__ size_t ps_off() const { return gs_off() + sizeof(T) * NS * GPS * 32; }
     __host__ __device__ size_t bar_off() const { return (ps_off() + sizeof(T) * 2 * NS * 32 + 15) & ~(size_t)15; }
-    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB); }
+    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB + 4); }
 };
 
 }  // namespace ru
+
+// one sample of one lane, bit-exact (src/filterbank.h:178-179).  TAPS: 0 general; 1: b1 == 0; 2: b1 == 0 and
+// b2 == -b0 (the skipped operations are exact identities, see filterbank_ws.inc).
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ T ru_sample(T x0, T b0, T b1, T b2, T a1, T a2, T p, T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2) {
+    typedef Ar<T, FMA> A;
+    T fw;
+    if (TAPS == 2 && !FMA) {
+        const T m0 = A::mul(b0, x0);
+        fw = A::sub(m0, m2);
+        m2 = m1; m1 = m0;
+    } else {
+        fw = A::mul(b0, x0);
+        if (TAPS == 0) fw = A::muladd(b1, x1, fw);
+        fw = A::muladd(b2, x2, fw);
+    }
+    T y;
+    if (FMA) {
+        const T fb = A::muladd(a2, y2, A::mul(a1, y1));
+        y = A::mulsub(fw, p, fb);
+    } else {
+        const T u = A::mul(fw, p);
+        const T fb = A::add(A::mul(a1, y1), t2);
+        y = A::sub(u, fb);
+        t2 = A::mul(a2, y1);
+    }
+    y2 = y1; y1 = y;
+    x2 = x1; x1 = x0;
+    return y;
+}
+
+// a full tile, unrolled; the next group's inputs are requested before this group is computed
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ void ru_tile(const T* __restrict__ xc, T* __restrict__ yrow, T b0, T b1, T b2, T a1, T a2, T p,
+                                        T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2) {
+    using namespace ru;
+    T xq[2][4];
+    ld4<T>(xc, xq[0]);
+#pragma unroll
+    for (int q = 0; q < TILE / 4; q++) {
+        if (q + 1 < TILE / 4) ld4<T>(xc + 4 * (q + 1), xq[(q + 1) & 1]);
+        T yy[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) yy[j] = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+        st4<T>(yrow + 4 * q, yy);
+    }
+}
 
 template <typename T> struct FbRuParams {
     FbK1Params<T> k;
@@ -117,6 +164,8 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
     unsigned long long* x_empty = bars + XB;                // [XB]
     unsigned long long* y_full = bars + 2 * XB;             // [W][NB]
     unsigned long long* y_empty = bars + 2 * XB + W * NB;   // [W][NB]
+    unsigned long long* ps_full = bars + 2 * XB + 2 * W * NB;       // [2] partial sums of S warps 1.. ready
+    unsigned long long* ps_empty = ps_full + 2;                      // [2] S warp 0 has consumed them
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cta = blockIdx.x, s = blockIdx.y;
@@ -134,6 +183,7 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
     if (threadIdx.x == 0) {
         for (int i = 0; i < XB; i++) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], w_here); }
         for (int i = 0; i < W * NB; i++) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&ps_full[i], NS - 1); mbar_init(&ps_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -153,7 +203,7 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
         const T cp = A::mul(P.c_p, pin), s_p = P.s_p;
         T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
         T m1 = A::mul(b0, x1), m2 = A::mul(b0, x2);         // taps == 2: fl(b0 x[t-1]), fl(b0 x[t-2])
-        const int taps = FMA ? 0 : P.taps;
+        const int taps = P.taps;
         bool conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
         T* ybase = ytiles + (size_t)warp * NB * 32 * RS + lane * RS;
         unsigned long long* yf = y_full + warp * NB;
@@ -169,76 +219,17 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
             int tt = 0;
             if (conv && tn == TILE) {
-                // whole tile unrolled; the next group's inputs are requested before this group is computed
-                T xq[2][4];
-                ld4<T>(xc, xq[0]);
-#pragma unroll
-                for (int q = 0; q < TILE / 4; q++) {
-                    if (q + 1 < TILE / 4) ld4<T>(xc + 4 * (q + 1), xq[(q + 1) & 1]);
-                    const T(&xv)[4] = xq[q & 1];
-                    T yy[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const T x0 = xv[j];
-                        T fw;
-                        if (taps == 2) {                    // b1 == 0, b2 == -b0: exact identities skipped
-                            const T m0 = A::mul(b0, x0);
-                            fw = A::sub(m0, m2);
-                            m2 = m1; m1 = m0;
-                        } else {
-                            fw = A::mul(b0, x0);                                   // filterbank.h:178
-                            if (taps == 0) fw = A::muladd(b1, x1, fw);
-                            fw = A::muladd(b2, x2, fw);
-                        }
-                        T y;
-                        if (FMA) {
-                            const T fb = A::muladd(a2, y2, A::mul(a1, y1));
-                            y = A::mulsub(fw, p, fb);
-                        } else {
-                            const T u = A::mul(fw, p);
-                            const T fb = A::add(A::mul(a1, y1), t2);              // filterbank.h:179
-                            y = A::sub(u, fb);
-                            t2 = A::mul(a2, y1);
-                        }
-                        y2 = y1; y1 = y;
-                        x2 = x1; x1 = x0;
-                        yy[j] = y;
-                    }
-                    st4<T>(yrow + 4 * q, yy);
-                }
+                // whole tile unrolled; `taps` is uniform, so pick the specialised body once per tile
+                if (taps == 2) ru_tile<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+                else if (taps == 1) ru_tile<T, FMA, 1>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+                else ru_tile<T, FMA, 0>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                 tt = TILE;
             } else if (conv) {
                 for (; tt + 4 <= tn; tt += 4) {
-                    T xv[4];
+                    T xv[4], yy[4];
                     ld4<T>(xc + tt, xv);
-                    T yy[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const T x0 = xv[j];
-                        T fw;
-                        if (taps == 2) {                    // b1 == 0, b2 == -b0: exact identities skipped
-                            const T m0 = A::mul(b0, x0);
-                            fw = A::sub(m0, m2);
-                            m2 = m1; m1 = m0;
-                        } else {
-                            fw = A::mul(b0, x0);                                   // filterbank.h:178
-                            if (taps == 0) fw = A::muladd(b1, x1, fw);
-                            fw = A::muladd(b2, x2, fw);
-                        }
-                        T y;
-                        if (FMA) {
-                            const T fb = A::muladd(a2, y2, A::mul(a1, y1));
-                            y = A::mulsub(fw, p, fb);
-                        } else {
-                            const T u = A::mul(fw, p);
-                            const T fb = A::add(A::mul(a1, y1), t2);              // filterbank.h:179
-                            y = A::sub(u, fb);
-                            t2 = A::mul(a2, y1);
-                        }
-                        y2 = y1; y1 = y;
-                        x2 = x1; x1 = x0;
-                        yy[j] = y;
-                    }
+                    for (int j = 0; j < 4; j++) yy[j] = ru_sample<T, FMA, 0>(xv[j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                     st4<T>(yrow + tt, yy);
                 }
             }
@@ -255,7 +246,7 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
                 x2 = x1; x1 = x0;
                 yrow[tt] = y;
             }
-            if (!conv || (tn & 3)) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
+            if (!conv || tn != TILE) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
             if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
             __syncwarp();
             const bool chunk_done = (kc == TPC - 1) || (k == ntiles - 1);
@@ -353,10 +344,12 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
                     const T* gw = gs + i * 32;
 #pragma unroll
                     for (int l = 0; l < 32; l += 4) {
-                        a0 = A::acc(yt[(l + 0) * RS], gw[l + 0], a0);
-                        a1s = A::acc(yt[(l + 1) * RS], gw[l + 1], a1s);
-                        a2s = A::acc(yt[(l + 2) * RS], gw[l + 2], a2s);
-                        a3 = A::acc(yt[(l + 3) * RS], gw[l + 3], a3);
+                        T g4[4];
+                        ld4<T>(gw + l, g4);                                  // broadcast, one LDS per 4 filters
+                        a0 = A::acc(yt[(l + 0) * RS], g4[0], a0);
+                        a1s = A::acc(yt[(l + 1) * RS], g4[1], a1s);
+                        a2s = A::acc(yt[(l + 2) * RS], g4[2], a2s);
+                        a3 = A::acc(yt[(l + 3) * RS], g4[3], a3);
                     }
                 }
                 acc += (a0 + a1s) + (a2s + a3);
@@ -370,16 +363,24 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kern
             }
             if (!gconv) gconv = !__any_sync(0xffffffffu, still);
             if (out_row) {
-                // combine the S warps' partial sums in fixed order; one named barrier per tile (the
-                // psum buffers alternate, so the next write to this buffer is two barriers away)
-                T* ps = psum + (size_t)(k & 1) * NS * 32;
-                ps[sidx * 32 + lane] = acc;
-                asm volatile("bar.sync 1, %0;" ::"n"(NS * 32) : "memory");
-                if (sidx == 0 && lane < tn) {
-                    T tot = ps[lane];
+                // combine the S warps' partial sums in fixed order through a 2-deep mbarrier hand-over:
+                // S warps 1.. publish and move on, S warp 0 adds the rows in order and writes the CTA's row
+                const int pb = k & 1;
+                const unsigned ppar = (unsigned)((k >> 1) & 1);
+                T* ps = psum + (size_t)pb * NS * 32;
+                if (sidx != 0) {
+                    mbar_wait(&ps_empty[pb], ppar ^ 1u);
+                    ps[sidx * 32 + lane] = acc;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ps_full[pb]);
+                } else {
+                    mbar_wait(&ps_full[pb], ppar);
+                    T tot = acc;
 #pragma unroll
                     for (int i = 1; i < NS; i++) tot += ps[i * 32 + lane];
-                    out_row[tg + lane] = tot;
+                    if (lane < tn) out_row[tg + lane] = tot;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ps_empty[pb]);
                 }
             }
             if (++yb == NB) { yb = 0; ypar ^= 1u; }
