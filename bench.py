@@ -38,6 +38,8 @@ WORKLOADS = {
     # the per-GPU shards of configs[2] at 8 and 4 GPUs
     "c3_8192": dict(N=8192, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
     "c3_16384": dict(N=16384, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
+    # BASELINE configs[3] without the envelope followers: 1024 independent streams x 1024 filters, 1 s blocks
+    "c4": dict(N=1024, streams=1024, seconds=1, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="white"),
 }
 
 
@@ -66,7 +68,7 @@ def bank_params(w, rank, world):
 
 def make_bank(cls, w, rank, world, dtype, **kw):
     fwd, back, gains = bank_params(w, rank, world)
-    fb = cls(2, w["N"], w["k_p"], w["k_g"], dtype=dtype, **kw)
+    fb = cls(2, w["N"], w["k_p"], w["k_g"], dtype=dtype, streams=w.get("streams", 1), **kw)
     fb.coefficients(0, fwd, back)
     fb.mix(gains)
     fb.boost(np.ones(w["N"]))
@@ -75,9 +77,13 @@ def make_bank(cls, w, rank, world, dtype, **kw):
 
 def synth_input(w, L, dtype):
     from huygens_b200 import design
+    S = w.get("streams", 1)
     if w["input"] == "chirp":
-        return design.chirp(L, dtype=dtype)
-    return design.white_noise(L, dtype=dtype)
+        x = design.chirp(L, dtype=dtype)
+        return x if S == 1 else np.tile(x, (S, 1))
+    if S == 1:
+        return design.white_noise(L, dtype=dtype)
+    return np.stack([design.white_noise(L, stream=s, dtype=dtype) for s in range(S)])
 
 
 class ClockSampler:
@@ -215,10 +221,11 @@ def main():
     L = int(w["seconds"] * SR)
     N = w["N"]
     fb = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local)
+    S = w.get("streams", 1)
     x_host = torch.from_numpy(synth_input(w, L, dtype)).pin_memory()
-    out_host = torch.empty(L, dtype=tdtype).pin_memory()
+    out_host = torch.empty(x_host.shape, dtype=tdtype).pin_memory()
     x = x_host.cuda(non_blocking=True)
-    out = torch.empty(L, dtype=tdtype, device="cuda")
+    out = torch.empty(x_host.shape, dtype=tdtype, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak = hb.fma_peak(np.float32, device=local)
 
@@ -285,7 +292,7 @@ def main():
     # side measurement (N = 1 only): the same block through the time-parallel scan, whose result is
     # tolerance-bounded instead of bit-identical
     scan_info = None
-    if world == 1 and args.mode == "exact" and not args.no_scan:
+    if world == 1 and args.mode == "exact" and not args.no_scan and S == 1:
         out_exact = out.clone()
         for _ in range(3):
             fb.process(x, out=out, mode="scan")
@@ -308,9 +315,9 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    units = float(N) * world * L * args.steps
+    units = float(N) * S * world * L * args.steps
     value = units / t_total
-    per_gpu_kernel = float(N) * L * args.steps / t_kernel
+    per_gpu_kernel = float(N) * S * L * args.steps / t_kernel
     achieved = per_gpu_kernel * SLOTS_PER_FILTER_SAMPLE
     nominal = peak["sm_count"] * 128 * 1.965e9
     traffic = None
@@ -326,7 +333,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(w, args, world),
-        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(L * 4), "d2h_bytes_per_step": int(L * 4)},
+        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * 4), "d2h_bytes_per_step": int(S * L * 4)},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",

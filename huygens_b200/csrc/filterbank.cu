@@ -332,7 +332,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
     // segment the block so the partial-sum scratch stays bounded
     size_t seg = L;
     if (rows > 1 && d_out) {
-        const size_t budget = (size_t)256 << 20;
+        const size_t budget = (size_t)1024 << 20;     // partial-sum scratch: 1 GiB of the 180 GB
         size_t per_sample = (size_t)rows * fb->S * sizeof(T);
         size_t max_seg = budget / per_sample;
         max_seg = max_seg < 4096 ? 4096 : (max_seg / 1024) * 1024;

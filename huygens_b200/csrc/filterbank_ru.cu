@@ -25,9 +25,10 @@ constexpr int NB = 2;         // tile ring depth per RU warp
 constexpr int XT = 1024;      // input chunk
 constexpr int XB = 2;         // input ring depth
 constexpr int W_MAX = 14;     // RU warps per CTA
-constexpr int NS = 7;         // S warps per CTA (each serves at most 2 RU warps: an S warp must not need more than its
-                              // fair share of its scheduler's issue slots, or the RU warps starve behind it)
-constexpr int GPS = (W_MAX + NS - 1) / NS;   // RU warps served by one S warp, at most
+constexpr int GPS = 2;        // RU warps served by one S warp: an S warp must not need more than its fair share
+                              // of its scheduler's issue slots, or the RU warps starve behind it
+constexpr int NS_MAX = (W_MAX + GPS - 1) / GPS;
+__host__ __device__ constexpr int s_warps(int W) { return (W + GPS - 1) / GPS; }
 
 template <typename T> struct RowStride;      // RS*sizeof(T)/16 odd: conflict-free 128-bit rows
 template <> struct RowStride<float> { static constexpr int RS = TILE + 4; };
@@ -79,8 +80,8 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
 //   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[2][NS][32] | barriers
 template <typename T> struct Layout {
     static constexpr int RS = RowStride<T>::RS;
-    int W;
-    __host__ __device__ explicit Layout(int w) : W(w) {}
+    int W, NS;
+    __host__ __device__ explicit Layout(int w) : W(w), NS(s_warps(w)) {}
     __host__ __device__ size_t xs_off() const { return 0; }
     __host__ __device__ size_t y_off() const { return sizeof(T) * XB * XT; }
     __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NB * 32 * RS; }
@@ -146,12 +147,13 @@ template <typename T> struct FbRuParams {
 };
 
 template <typename T, bool FMA, bool BANDS>
-__global__ void __launch_bounds__((ru::W_MAX + ru::NS) * 32, 1) fb_exact_ru_kernel(FbRuParams<T> Q) {
+__global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
     constexpr int RS = RowStride<T>::RS;
     const FbK1Params<T>& P = Q.k;
     const int W = Q.W;
+    const int NS = s_warps(W);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Layout<T> lay(W);
     T* xs = reinterpret_cast<T*>(smem_raw + lay.xs_off());
@@ -430,7 +432,7 @@ static hg_status launch_ru(const FbK1Params<T>& P, int W, int cps, cudaStream_t 
     const size_t smem = ru::Layout<T>(W).bytes();
     auto kern = fb_exact_ru_kernel<T, FMA, BANDS>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(cps, P.S), (W + ru::NS) * 32, smem, st>>>(Q);
+    kern<<<dim3(cps, P.S), (W + ru::s_warps(W)) * 32, smem, st>>>(Q);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
