@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 SR = 48000
 SLOTS_PER_FILTER_SAMPLE = 11        # 11 mul + 7 add, every add fusable: SURVEY.md §8(d)
 WORKLOADS = {
+    # BASELINE configs[0]: Filterbank<double>, 64 resonant band-passes (resynthesis recipe), 10 s white noise
+    "c1": dict(N=64, seconds=10, f_lo=369.0, f_hi=23630.0, r=0.999, k_p=0.1, k_g=1.0, input="white", dtype="f64"),
     # name: (filters per GPU, seconds, f_lo, f_hi, r, k_p, k_g, input)
     "c2": dict(N=4096, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
     # BASELINE configs[2] (65,536 filters; a parity/scaling case, not the headline): 10 s blocks
@@ -191,7 +193,9 @@ def run_reference(args, w, rank, world):
 
 
 def workload_config(w, args, world):
-    return {"workload": f"Filterbank<float> {w['N']} log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, "
+    tname = "double" if w.get("dtype") == "f64" else "float"
+    sname = f"{w['streams']} streams x " if w.get("streams", 1) > 1 else ""
+    return {"workload": f"Filterbank<{tname}> {sname}{w['N']} log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, "
                         f"fwd {{1,0,-1}}, k_p={w['k_p']}, k_g={w['k_g']}), {w['seconds']} s 48 kHz {w['input']}, summed output",
             "filters_per_gpu": w["N"], "filters_total": w["N"] * world, "samples": int(w["seconds"] * SR),
             "partition": "filters" if world > 1 else "none", "mode": args.mode, "arith": args.arith,
@@ -217,7 +221,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dtype, tdtype = np.float32, torch.float32
+    dtype, tdtype = (np.float64, torch.float64) if w.get("dtype") == "f64" else (np.float32, torch.float32)
     L = int(w["seconds"] * SR)
     N = w["N"]
     fb = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local)
@@ -227,7 +231,7 @@ def main():
     x = x_host.cuda(non_blocking=True)
     out = torch.empty(x_host.shape, dtype=tdtype, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    peak = hb.fma_peak(np.float32, device=local)
+    peak = hb.fma_peak(dtype, device=local)
 
     def step():
         fb.process(x, out=out, mode=args.mode)
@@ -331,9 +335,9 @@ def main():
     line = {
         "metric": "filter-samples/s (biquad bank)", "value": value, "unit": "filter-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.get("dtype", "f32"), "data": "synthetic",
         "config": workload_config(w, args, world),
-        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * 4), "d2h_bytes_per_step": int(S * L * 4)},
+        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * x_host.element_size()), "d2h_bytes_per_step": int(S * L * x_host.element_size())},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
