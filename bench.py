@@ -232,6 +232,7 @@ def main():
     out = torch.empty(x_host.shape, dtype=tdtype, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak = hb.fma_peak(dtype, device=local)
+    chain_cycles = hb.chain_latency(dtype, device=local)
 
     def step():
         fb.process(x, out=out, mode=args.mode)
@@ -344,7 +345,10 @@ def main():
                      "frac": achieved / peak["slots_per_s"], "traffic": traffic,
                      "peak_source": "hg_fma_peak FFMA microbenchmark, measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                      "frac_of_nominal": achieved / nominal, "slots_per_unit": SLOTS_PER_FILTER_SAMPLE,
-                     "kernel_ms": t_kernel / args.steps * 1e3, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
+                     "kernel_ms": t_kernel / args.steps * 1e3,
+                     # bit-exact ceiling: every lane must run the FMUL->FADD->FADD chain once per sample, serially
+                     "chain_cycles_per_sample_measured": chain_cycles,
+                     "bit_exact_floor_ms": L * chain_cycles / (peak["sm_mhz"] * 1e3) if peak["sm_mhz"] else None, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
                      "ctas": info["ctas"]},
     }
     if scan_info:

@@ -4,6 +4,7 @@
 #include "../include/huygens/filterbank.h"
 #include "../include/huygens/oscbank.h"
 #include "../include/huygens/rmsbank.h"
+#include "../include/huygens/latchbank.h"
 
 using namespace soundmath;
 
@@ -14,6 +15,8 @@ int main(int argc, char** argv) {
     try {
         Oscbank<double, 8> osc;
         RMSbank<double, 8> rms(16);
+        RMSbank<double, 8> rms2(16);
+        Latchbank<double, 8> latch(0.9, 0.2);        // tests/rmsbank.cpp:15
         FFilterbank<double, 4, 2> F(0.001, 1);
         for (int i = 0; i < 8; i++) osc.freqmod(i, 110.0 * (i + 1));
         osc.freqmod(99, 1.0);       // ignored, oscbank.h:51
@@ -30,8 +33,11 @@ int main(int argc, char** argv) {
             const std::complex<double> m = osc.mixdown();
             const double y = F(m.real());
             const double yd = F(m.real(), &softclip);
-            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd);
-            osc.tick(); rms.tick(); F.tick();
+            const auto* gated = latch(&rms2, ph);               // tests/harmbank.cpp:84-86
+            double gsum = 0;
+            for (int i = 0; i < 8; i++) gsum += (*gated)(i).real();
+            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum);
+            osc.tick(); rms.tick(); rms2.tick(); F.tick();
         }
     } catch (const cuda_error& e) {
         std::fprintf(stderr, "huygens_cuda error %d: %s\n", e.status, e.what());

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("hg_last_error", C.c_char_p, []),
     ("hg_device_count", _i, []),
     ("hg_fma_peak", _i, [_i, _i, _pd, _pi, _pd]),
+    ("hg_chain_latency", _i, [_i, _i, _pd]),
     ("hg_fb_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _d, _d, _i, _i]),
     ("hg_fb_destroy", _i, [_vp]),
     ("hg_fb_set_coefficients", _i, [_vp, _i, _i, _vp, _i, _vp, _i]),
@@ -49,6 +50,8 @@ SYMBOLS = [
     ("hg_rms_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     ("hg_rms_destroy", _i, [_vp]),
     ("hg_rms_process", _i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    ("hg_rms_set_latch", _i, [_vp, _d, _d]),
+    ("hg_rms_process_latch", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 ]
 
 

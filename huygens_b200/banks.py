@@ -262,8 +262,38 @@ class RMSbank(_Handle):
         return out
 
 
+class Latchbank:
+    """Latchbank<T,N>(thresh, ratio) gating its RMSbank<T,N>(width) — src/latchbank.h:16-105, used as
+    `latchbank(&rmsbank, signal)` (tests/harmbank.cpp:84-99)."""
+
+    def __init__(self, N, thresh, ratio=0.2, width=2400, dtype=np.float64, arith="strict", device=0):
+        self.rms = RMSbank(N, width, dtype=dtype, arith=arith, device=device)
+        self.N, self.dtype = N, self.rms.dtype
+        L.check(L.lib().hg_rms_set_latch(self.rms._h, float(thresh), float(ratio)))
+
+    def process(self, zre, zim=None, level=False):
+        """zre/zim [N][L]; returns gated re (, gated im) (, level)."""
+        zre = np.ascontiguousarray(zre, dtype=self.dtype)
+        zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
+        ore = np.empty_like(zre)
+        oim = None if zim is None else np.empty_like(zre)
+        lv = np.empty_like(zre) if level else None
+        L.check(L.lib().hg_rms_process_latch(self.rms._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), _ptr(lv), zre.shape[1], None))
+        res = [ore] if zim is None else [ore, oim]
+        if level:
+            res.append(lv)
+        return res[0] if len(res) == 1 else tuple(res)
+
+
 def fma_peak(dtype=np.float32, device=0):
     """Measured FMA issue rate (lane-FMA slots/s), SM count and SM clock (MHz) of `device`."""
     s, n, m = C.c_double(), C.c_int(), C.c_double()
     L.check(L.lib().hg_fma_peak(device, _NP2HG[np.dtype(dtype)], C.byref(s), C.byref(n), C.byref(m)))
     return dict(slots_per_s=s.value, sm_count=n.value, sm_mhz=m.value)
+
+
+def chain_latency(dtype=np.float32, device=0):
+    """Measured cycles per sample of the bit-exact recurrence chain (FMUL -> FADD -> FADD) of one lane."""
+    c = C.c_double()
+    L.check(L.lib().hg_chain_latency(device, _NP2HG[np.dtype(dtype)], C.byref(c)))
+    return c.value

@@ -70,6 +70,52 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* sink, int iters, T a, 
     if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = c1 - c0; clk[1] = (long long)(g1 - g0); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dependent-chain microbenchmark: one warp per scheduler runs the biquad recurrence's critical path
+//     y <- fl(u - fl(fl(a1*y) + t2))        FMUL -> FADD -> FADD, each consuming the previous result
+// with nothing else to issue.  Cycles per iteration is the floor of ANY bit-exact serial evaluation of
+// one filter lane (the arithmetic may not be re-associated or fused), measured instead of assumed.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) chain_kernel(T* sink, int iters, T a1, T u, T t2, long long* clk) {
+    T y = (T)threadIdx.x * (T)1e-3;
+    const long long c0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (sizeof(T) == 4) y = (T)__fsub_rn((float)u, __fadd_rn(__fmul_rn((float)a1, (float)y), (float)t2));
+            else y = (T)__dsub_rn((double)u, __dadd_rn(__dmul_rn((double)a1, (double)y), (double)t2));
+        }
+    }
+    const long long c1 = clock64();
+    if (y == (T)123456789) sink[0] = y;
+    if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = c1 - c0;
+}
+
+template <typename T>
+static hg_status chain_T(int device, double* cycles_per_step) {
+    HG_CUDA(cudaSetDevice(device));
+    T* sink;
+    long long* clk;
+    HG_CUDA(cudaMalloc(&sink, sizeof(T)));
+    HG_CUDA(cudaMalloc(&clk, sizeof(long long)));
+    const int iters = 4096;
+    double best = 1e30;
+    for (int rep = 0; rep < 4; rep++) {
+        chain_kernel<T><<<1, 128>>>(sink, iters, (T)0.999, (T)0.5, (T)0.25, clk);
+        HG_CUDA(cudaDeviceSynchronize());
+        long long cyc = 0;
+        HG_CUDA(cudaMemcpy(&cyc, clk, sizeof(cyc), cudaMemcpyDeviceToHost));
+        const double c = (double)cyc / ((double)iters * 16.0);
+        if (c < best) best = c;
+    }
+    *cycles_per_step = best;
+    cudaFree(sink);
+    cudaFree(clk);
+    return HG_OK;
+}
+
 template <typename T>
 static hg_status fma_peak_T(int device, double* slots, int* sms, double* mhz) {
     HG_CUDA(cudaSetDevice(device));
@@ -124,6 +170,13 @@ int hg_device_count(void) {
         return 0;
     }
     return n;
+}
+
+hg_status hg_chain_latency(int device, int dtype, double* cycles_per_sample) {
+    if (!cycles_per_sample) return hg::fail(HG_ERR_INVALID, "hg_chain_latency: null output");
+    if (dtype == HG_F32) return hg::chain_T<float>(device, cycles_per_sample);
+    if (dtype == HG_F64) return hg::chain_T<double>(device, cycles_per_sample);
+    return hg::fail(HG_ERR_INVALID, "hg_chain_latency: bad dtype %d", dtype);
 }
 
 hg_status hg_fma_peak(int device, int dtype, double* slots_per_s, int* sm_count, double* sm_mhz) {

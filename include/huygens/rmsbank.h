@@ -41,6 +41,11 @@ public:
     void process(const T* zre, const T* zim, T* result, size_t L, void* cuda_stream = nullptr) {
         hg_check(hg_rms_process(rms, zre, zim, result, L, cuda_stream));
     }
+    // new: L ticks of `gated = latchbank(&rmsbank, z); rmsbank.tick();` (latchbank.h:81-100) fused on the device
+    void set_latch(T thresh, T ratio = 0.2) { hg_check(hg_rms_set_latch(rms, (double)thresh, (double)ratio)); }
+    void process_latch(const T* zre, const T* zim, T* gated_re, T* gated_im, size_t L, T* level = nullptr, void* cuda_stream = nullptr) {
+        hg_check(hg_rms_process_latch(rms, zre, zim, gated_re, gated_im, level, L, cuda_stream));
+    }
 
 private:
     hg_rms* rms = nullptr;

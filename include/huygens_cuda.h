@@ -54,6 +54,9 @@ int hg_device_count(void);
  * from a register-resident FFMA/DFMA microbenchmark; also returns SM count and the SM clock (MHz)
  * observed during it.  This is the denominator of the FMA roofline. */
 hg_status hg_fma_peak(int device, int dtype, double* slots_per_s, int* sm_count, double* sm_mhz);
+/* Measured cycles per sample of the recurrence's dependency chain y <- fl(u - fl(fl(a1*y) + t2)) for one
+ * warp alone on its scheduler: the floor of any bit-exact serial evaluation of one filter lane. */
+hg_status hg_chain_latency(int device, int dtype, double* cycles_per_sample);
 
 /* ---- Filterbank<T> / FFilterbank<T,N,order>  (src/filterbank.h) -------------------------- */
 /* Filterbank(int order, int N, double k_p, double k_g)  src/filterbank.h:36-70; n_streams
@@ -119,6 +122,15 @@ hg_status hg_rms_destroy(hg_rms* rms);
  * zre, zim, out: [n_channels][L] channel-major; zim may be NULL (real input). */
 hg_status hg_rms_process(hg_rms* rms, const void* zre, const void* zim, void* out, size_t L,
                          void* cuda_stream);
+
+/* ---- Latchbank<T,N>  (src/latchbank.h) ------------------------------------------------------- */
+/* Latchbank(T thresh, T ratio) src/latchbank.h:34-53, attached to this RMSbank handle (flags reset). */
+hg_status hg_rms_set_latch(hg_rms* rms, double thresh, double ratio);
+/* L ticks of `gated = latch(&rms, z); rms.tick();` (latchbank.h:81-100, tests/harmbank.cpp:84-99):
+ * out_re/out_im [n_channels][L] = z * engaged; out_level (nullable) = the RMS level that drove the gate.
+ * zim / out_im may both be NULL (real signal). */
+hg_status hg_rms_process_latch(hg_rms* rms, const void* zre, const void* zim, void* out_re, void* out_im,
+                               void* out_level, size_t L, void* cuda_stream);
 
 #ifdef __cplusplus
 }

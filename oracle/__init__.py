@@ -64,6 +64,11 @@ def lib():
             f("hgo_rms_create").argtypes = [C.c_int, C.c_int, C.c_int]
             f("hgo_rms_destroy").argtypes = [C.c_void_p]
             f("hgo_rms_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+            f("hgo_latch_create").restype = C.c_void_p
+            f("hgo_latch_create").argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+            f("hgo_latch_destroy").argtypes = [C.c_void_p]
+            f("hgo_latch_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+            f("hgo_latch_process_real").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
     return _LIB
 
 
@@ -213,6 +218,38 @@ class RMSbank(_Base):
         return out
 
 
+class Latchbank(_Base):
+    """Latchbank<T,N>(thresh, ratio) gating an RMSbank<T,N>(width) — latchbank.h:16-105.
+    process(): per tick gated = latch(&rms, z); rms.tick().  process_real(): out = latch(level)."""
+
+    def __init__(self, N, thresh, ratio=0.2, width=2400, dtype=np.float64, mode="strict"):
+        super().__init__(dtype, mode)
+        self.N = N
+        self._h = self._f("hgo_latch_create")(DTYPES[self.dtype], N, width, float(thresh), float(ratio))
+
+    def __del__(self):
+        if self._h:
+            self._f("hgo_latch_destroy")(self._h)
+            self._h = None
+
+    def process(self, zre, zim=None, level=False):
+        zre = np.ascontiguousarray(zre, dtype=self.dtype)
+        zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
+        ore, oim = np.empty_like(zre), (None if zim is None else np.empty_like(zre))
+        lv = np.empty_like(zre) if level else None
+        self._f("hgo_latch_process")(self._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), _ptr(lv), zre.shape[1])
+        res = [ore] if zim is None else [ore, oim]
+        if level:
+            res.append(lv)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def process_real(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        out = np.empty_like(x)
+        self._f("hgo_latch_process_real")(self._h, _ptr(x), _ptr(out), x.shape[1])
+        return out
+
+
 # ---------------------------------------------------------------------------------------------
 # oracle/_ref: the UNMODIFIED reference headers compiled against oracle/shim (see ref_capi.cpp).
 # Used only to pin the restatement above (tests/test_oracle_vs_ref.py).
@@ -248,6 +285,9 @@ def ref_lib():
             "hgr_osc_get_phases": (None, [vp, vp]),
             "hgr_rms_create": (vp, [i, i, i]), "hgr_rms_destroy": (None, [vp]),
             "hgr_rms_process": (None, [vp, vp, vp, vp, lg, i]),
+            "hgr_latch_create": (vp, [i, i, i, d, d]), "hgr_latch_destroy": (None, [vp]),
+            "hgr_latch_process": (None, [vp, vp, vp, vp, vp, vp, lg]),
+            "hgr_latch_process_real": (None, [vp, vp, vp, lg]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(_REF, name)
@@ -364,4 +404,36 @@ class RefRMSbank:
         zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
         out = np.empty_like(zre)
         ref_lib().hgr_rms_process(self._h, _ptr(zre), _ptr(zim), _ptr(out), zre.shape[1], calls_per_tick)
+        return out
+
+
+class RefLatchbank:
+    """soundmath::Latchbank<T,N>(thresh, ratio) with its RMSbank<T,N>(width), N in REF_RMS_N."""
+
+    def __init__(self, N, thresh, ratio=0.2, width=2400, dtype=np.float64):
+        self.dtype, self.N = np.dtype(dtype), N
+        self._h = ref_lib().hgr_latch_create(DTYPES[self.dtype], N, width, float(thresh), float(ratio))
+        if not self._h:
+            raise ValueError("this Latchbank<T,N> is not instantiated in ref_capi.cpp")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().hgr_latch_destroy(self._h)
+            self._h = None
+
+    def process(self, zre, zim=None, level=False):
+        zre = np.ascontiguousarray(zre, dtype=self.dtype)
+        zim = None if zim is None else np.ascontiguousarray(zim, dtype=self.dtype)
+        ore, oim = np.empty_like(zre), (None if zim is None else np.empty_like(zre))
+        lv = np.empty_like(zre) if level else None
+        ref_lib().hgr_latch_process(self._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), _ptr(lv), zre.shape[1])
+        res = [ore] if zim is None else [ore, oim]
+        if level:
+            res.append(lv)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def process_real(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        out = np.empty_like(x)
+        ref_lib().hgr_latch_process_real(self._h, _ptr(x), _ptr(out), x.shape[1])
         return out

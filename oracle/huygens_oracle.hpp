@@ -302,4 +302,43 @@ public:
     std::vector<T> inputs, out, lastout;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Latchbank<T,N>  (src/latchbank.h:16-105): hysteresis gate driven by a level (an RMSbank output).
+// Per channel: armed |= in < thresh*ratio; a channel that is engaged and falls below thresh*ratio
+// disengages and disarms; a channel that is not engaged, is armed and rises above thresh*(1-ratio)
+// engages.  Output = input (or the complex signal) times the 0/1 `engaged` flag.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class Latchbank : public Multichannel {
+public:
+    Latchbank(int N, T thresh, T ratio) : Multichannel(N), thresh(thresh), ratio(ratio), armed(N, 0), engaged(N, 0), out(N, 0) {}   // :34-53
+    // :61-79
+    const T* operator()(const T* input) {
+        step(input);
+        for (int n = 0; n < N; n++) out[n] = input[n] * (T)engaged[n];
+        return out.data();
+    }
+    // :81-100  level = rms(signal) (first evaluation of the tick, in-place sqrt included); gated complex out
+    void operator()(RMSbank<T, FMA>& rms, const T* zre, const T* zim, T* ore, T* oim) {
+        const T* level = rms(zre, zim);
+        step(level);
+        for (int n = 0; n < N; n++) { ore[n] = zre[n] * (T)engaged[n]; oim[n] = zim[n] * (T)engaged[n]; }
+    }
+    std::vector<char> armed, engaged;
+    T thresh, ratio;
+
+private:
+    std::vector<T> out;
+    void step(const T* in) {
+        const T lo = thresh * ratio, hi = thresh * ((T)1 - ratio);
+        for (int n = 0; n < N; n++) {
+            armed[n] = armed[n] || (in[n] < lo);                                   // :63 / :85
+            const bool t1 = engaged[n] && (in[n] < lo);                            // :65 / :87
+            const bool t2 = !engaged[n] && (in[n] > hi) && armed[n];               // :66 / :88
+            engaged[n] = engaged[n] && !t1;                                        // :69 / :91
+            armed[n] = armed[n] && !t1;                                            // :70 / :92
+            engaged[n] = engaged[n] || t2;                                         // :73 / :95
+        }
+    }
+};
+
 }  // namespace hgoracle

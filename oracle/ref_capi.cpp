@@ -21,6 +21,7 @@
 #include HG_STR(HG_REF_SRC/filterbank.h)
 #include HG_STR(HG_REF_SRC/oscbank.h)
 #include HG_STR(HG_REF_SRC/rmsbank.h)
+#include HG_STR(HG_REF_SRC/latchbank.h)
 #undef private
 #undef protected
 
@@ -135,6 +136,51 @@ template <typename T, int N> struct RmsImpl : RmsBase {
     }
 };
 
+struct LatchBase {
+    virtual ~LatchBase() {}
+    virtual void process(const void* zre, const void* zim, void* ore, void* oim, void* level, long L) = 0;
+    virtual void process_real(const void* in, void* out, long L) = 0;
+};
+template <typename T, int N> struct LatchImpl : LatchBase {
+    RMSbank<T, N> rms;
+    Latchbank<T, N> latch;
+    LatchImpl(int width, double thresh, double ratio) : rms((uint)width), latch((T)thresh, (T)ratio) {}
+    // tests/harmbank.cpp:84-99: latchbank(&rmsbank, signal) ... rmsbank.tick()
+    void process(const void* zre_, const void* zim_, void* ore_, void* oim_, void* level_, long L) override {
+        const T* zre = (const T*)zre_; const T* zim = (const T*)zim_; T* ore = (T*)ore_; T* oim = (T*)oim_; T* lv = (T*)level_;
+        Eigen::Array<std::complex<T>, Eigen::Dynamic, 1> z;
+        z.resize(N);
+        for (long t = 0; t < L; t++) {
+            for (int n = 0; n < N; n++) z(n) = std::complex<T>(zre[(size_t)n * L + t], zim ? zim[(size_t)n * L + t] : (T)0);
+            const auto* o = latch(&rms, &z);
+            for (int n = 0; n < N; n++) {
+                ore[(size_t)n * L + t] = (*o)(n).real();
+                if (oim) oim[(size_t)n * L + t] = (*o)(n).imag();
+                if (lv) lv[(size_t)n * L + t] = (*rms.out)(n);
+            }
+            rms.tick();
+        }
+    }
+    void process_real(const void* in_, void* out_, long L) override {
+        const T* in = (const T*)in_; T* out = (T*)out_;
+        Eigen::Array<T, Eigen::Dynamic, 1> a;
+        a.resize(N);
+        for (long t = 0; t < L; t++) {
+            for (int n = 0; n < N; n++) a(n) = in[(size_t)n * L + t];
+            const auto* o = latch(&a);
+            for (int n = 0; n < N; n++) out[(size_t)n * L + t] = (*o)(n);
+        }
+    }
+};
+template <typename T> LatchBase* make_latch(int N, int width, double thresh, double ratio) {
+    switch (N) {
+        case 1: return new LatchImpl<T, 1>(width, thresh, ratio);
+        case 8: return new LatchImpl<T, 8>(width, thresh, ratio);
+        case 40: return new LatchImpl<T, 40>(width, thresh, ratio);
+    }
+    return nullptr;
+}
+
 template <typename T> FbBase* make_fb(int fixed, int order, int N, double k_p, double k_g) {
     if (!fixed) return new FbImpl<T, DynAcc<T>>(new Filterbank<T>(order, N, k_p, k_g), N);
     if (order != 2) return nullptr;
@@ -192,4 +238,11 @@ void hgr_osc_get_phases(void* h, void* p) { ((OscBase*)h)->get_phases(p); }
 void* hgr_rms_create(int dtype, int N, int width) { return dtype == 0 ? (void*)make_rms<float>(N, width) : (void*)make_rms<double>(N, width); }
 void hgr_rms_destroy(void* h) { delete (RmsBase*)h; }
 void hgr_rms_process(void* h, const void* zre, const void* zim, void* out, long L, int calls) { ((RmsBase*)h)->process(zre, zim, out, L, calls); }
+
+void* hgr_latch_create(int dtype, int N, int width, double thresh, double ratio) {
+    return dtype == 0 ? (void*)make_latch<float>(N, width, thresh, ratio) : (void*)make_latch<double>(N, width, thresh, ratio);
+}
+void hgr_latch_destroy(void* h) { delete (LatchBase*)h; }
+void hgr_latch_process(void* h, const void* zre, const void* zim, void* ore, void* oim, void* level, long L) { ((LatchBase*)h)->process(zre, zim, ore, oim, level, L); }
+void hgr_latch_process_real(void* h, const void* in, void* out, long L) { ((LatchBase*)h)->process_real(in, out, L); }
 }

@@ -56,6 +56,16 @@ def rmsbank_case(dtype):
     return dict(N=N, width=width, zre=zre, zim=zim, out=out)
 
 
+def latchbank_case(dtype):
+    N, L, width = 8, 1500, 50
+    t = np.arange(L)
+    env = np.stack([0.5 * (1 + np.sin(2 * np.pi * t / (300.0 + 37 * n) + n)) for n in range(N)])
+    zre = (env * np.cos(0.3 * t)[None, :]).astype(dtype)
+    zim = (env * np.sin(0.3 * t)[None, :]).astype(dtype)
+    ore, oim, lv = oracle.RefLatchbank(N, 0.35, 0.2, width=width, dtype=dtype).process(zre, zim, level=True)
+    return dict(N=N, width=width, thresh=0.35, ratio=0.2, zre=zre, zim=zim, out_re=ore, out_im=oim, level=lv)
+
+
 def main():
     assert oracle.ref_lib() is not None, "oracle/_ref is not built"
     for dtype, tag in ((np.float32, "f32"), (np.float64, "f64")):
@@ -63,6 +73,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"filterbank_fixed_{tag}.npz"), **filterbank_case(dtype, True))
         np.savez_compressed(os.path.join(HERE, f"oscbank_{tag}.npz"), **oscbank_case(dtype))
         np.savez_compressed(os.path.join(HERE, f"rmsbank_{tag}.npz"), **rmsbank_case(dtype))
+        np.savez_compressed(os.path.join(HERE, f"latchbank_{tag}.npz"), **latchbank_case(dtype))
     print("written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

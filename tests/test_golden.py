@@ -34,7 +34,7 @@ def _run_fb(cls, g, dtype, **kw):
 
 
 def test_golden_files_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) == 8
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) == 10
 
 
 @pytest.mark.parametrize("tag,dtype", TAGS)
@@ -58,6 +58,24 @@ def test_oracle_reproduces_golden_osc_rms(oracle_lib, tag, dtype):
     g = np.load(os.path.join(GOLD, f"rmsbank_{tag}.npz"))
     out = oracle.RMSbank(int(g["N"]), int(g["width"]), dtype=dtype).process(g["zre"], g["zim"])
     assert same(out, g["out"])
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_oracle_reproduces_golden_latchbank(oracle_lib, tag, dtype):
+    g = np.load(os.path.join(GOLD, f"latchbank_{tag}.npz"))
+    lt = oracle.Latchbank(int(g["N"]), float(g["thresh"]), float(g["ratio"]), width=int(g["width"]), dtype=dtype)
+    ore, oim, lv = lt.process(g["zre"], g["zim"], level=True)
+    assert same(ore, g["out_re"]) and same(oim, g["out_im"]) and same(lv, g["level"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_cuda_reproduces_golden_latchbank(tag, dtype):
+    import huygens_b200 as hb
+    g = np.load(os.path.join(GOLD, f"latchbank_{tag}.npz"))
+    lt = hb.Latchbank(int(g["N"]), float(g["thresh"]), float(g["ratio"]), width=int(g["width"]), dtype=dtype)
+    ore, oim, lv = lt.process(g["zre"], g["zim"], level=True)
+    assert same(ore, g["out_re"]) and same(oim, g["out_im"]) and same(lv, g["level"])
 
 
 @pytest.mark.gpu

@@ -108,3 +108,27 @@ def test_rmsbank_restatement_equals_reference(oracle_lib, N, width, dtype, calls
     r = oracle.RefRMSbank(N, width, dtype=dtype).process(zre, zim, calls_per_tick=calls)
     m = oracle.RMSbank(N, width, dtype=dtype).process(zre, zim, calls_per_tick=calls)
     assert same(m, r)
+
+
+def _latch_signal(N, L, dtype):
+    t = np.arange(L)
+    env = np.stack([0.5 * (1 + np.sin(2 * np.pi * t / (300.0 + 37 * n) + n)) for n in range(N)])      # levels sweeping 0..1
+    zre = (env * np.cos(0.3 * t)[None, :]).astype(dtype)
+    zim = (env * np.sin(0.3 * t)[None, :]).astype(dtype)
+    return zre, zim
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,width", [(1, 7), (8, 50), (40, 240)])
+def test_latchbank_restatement_equals_reference(oracle_lib, N, width, dtype):
+    """Latchbank hysteresis gate driven by its RMSbank (src/latchbank.h:81-100, tests/harmbank.cpp:84-99)
+    and the real-input overload (:61-79)."""
+    L = 2500
+    zre, zim = _latch_signal(N, L, dtype)
+    r = oracle.RefLatchbank(N, 0.35, 0.2, width=width, dtype=dtype).process(zre, zim, level=True)
+    m = oracle.Latchbank(N, 0.35, 0.2, width=width, dtype=dtype).process(zre, zim, level=True)
+    for a, b in zip(m, r):
+        assert same(a, b)
+    assert 0.05 < np.mean(r[0] != 0) < 0.95                 # the gate both opens and closes
+    lv = np.abs(zre) + 0.01
+    assert same(oracle.Latchbank(N, 0.35, 0.3, dtype=dtype).process_real(lv), oracle.RefLatchbank(N, 0.35, 0.3, dtype=dtype).process_real(lv))
