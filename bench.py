@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=None, help="override block length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan", action="store_true", help="skip the scan-mode side measurement")
+    ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
 
 
@@ -234,8 +235,16 @@ def main():
     peak = hb.fma_peak(dtype, device=local)
     chain_cycles = hb.chain_latency(dtype, device=local)
 
+    env_buf = torch.empty((S, L // 64, N), dtype=tdtype, device="cuda") if args.env else None
+
+    def render(xi, oi):
+        if args.env:
+            fb.process_env(xi, width=2400, hop=64, out=oi, env=env_buf)
+        else:
+            fb.process(xi, out=oi, mode=args.mode)
+
     def step():
-        fb.process(x, out=out, mode=args.mode)
+        render(x, out)
         if world > 1:
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
 
@@ -257,7 +266,7 @@ def main():
         flush.fill_(i & 0xFF)                    # L2 flush, outside the timed events
         ev[i][0].record()
         kev[i][0].record()
-        fb.process(x, out=out, mode=args.mode)
+        render(x, out)
         kev[i][1].record()
         if world > 1:
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
@@ -351,6 +360,19 @@ def main():
                      "bit_exact_floor_ms": L * chain_cycles / (peak["sm_mhz"] * 1e3) if peak["sm_mhz"] else None, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
                      "ctas": info["ctas"]},
     }
+    if args.env:
+        # the fused envelope followers add 8 B of ring traffic per filter-sample (read q[t-width], write q[t]):
+        # that kernel is HBM-bound, so its roofline is the measured copy bandwidth
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+        except Exception:
+            hbm, src = 6650.0, "B200_PROFILING.md fallback"
+        gbs = per_gpu_kernel * 8 / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                            "peak_source": src, "bytes_per_unit": 8, "kernel_ms": t_kernel / args.steps * 1e3,
+                            "fma_frac": achieved / peak["slots_per_s"], "mode": info["mode"], "ctas": info["ctas"],
+                            "note": "Filterbank + per-band RMSbank(2400) followers, ring of y^2 in HBM; envelopes every 64 samples"}
     if scan_info:
         line["scan"] = scan_info
     if not args.no_cpu_baseline:

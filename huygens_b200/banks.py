@@ -137,6 +137,24 @@ class Filterbank(_Handle):
             return out, bd
         return out
 
+    def process_env(self, x, width=2400, hop=64, out=None, env=None):
+        """Block render + one RMSbank(width) envelope follower per (stream, filter), fused on the device.
+        Returns (out_sum, env[streams][L // hop][N]); env rows are block samples hop-1, 2*hop-1, ..."""
+        if _is_torch(x):
+            import torch
+            Ls = x.shape[-1]
+            out = torch.empty_like(x) if out is None else out
+            env = torch.empty((self.streams, Ls // hop, self.N), dtype=x.dtype, device=x.device) if env is None else env
+            stream = _torch_stream()
+        else:
+            x = np.ascontiguousarray(x, dtype=self.dtype)
+            Ls = x.shape[-1]
+            out = np.empty_like(x) if out is None else out
+            env = np.empty((self.streams, Ls // hop, self.N), self.dtype) if env is None else env
+            stream = None
+        L.check(L.lib().hg_fb_process_env(self._h, _ptr(x), _ptr(out), _ptr(env), Ls, width, hop, stream))
+        return out, env
+
     def process_bands(self, x, mode="exact"):
         """Per-band outputs only (no sum)."""
         x = np.ascontiguousarray(x, dtype=self.dtype)

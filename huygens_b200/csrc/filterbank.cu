@@ -289,6 +289,11 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     int level = 0;
     while (level < max_level && ws_ctas > ((long)fb->sm_count << level)) level++;
     const bool ws_fits = ws_ctas <= ((long)fb->sm_count << level);
+    if (fb->cur_env) {                   // fused envelope followers live in the RU/S kernel
+        *F_out = -2;
+        *groups_out = 0;
+        return;
+    }
     if (!fb->cur_dist && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
         fb->ws_level = level;
         *F_out = 0;
@@ -365,7 +370,15 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
         if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
-        else if (F == -2) rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st);
+        else if (F == -2) {
+            FbEnvArgs<T> E;
+            if (fb->cur_env) {
+                E.env = (T*)fb->cur_env_out; E.rms_sum = (T*)fb->d_rms_sum; E.rms_ring = (T*)fb->d_rms_ring;
+                E.width = fb->rms_width; E.hop = fb->cur_hop; E.env_rows = (long)fb->cur_env_rows;
+                E.t_base = (long)t0; E.tick0 = fb->rms_ticks;
+            }
+            rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st, fb->cur_env ? &E : nullptr);
+        }
         else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);

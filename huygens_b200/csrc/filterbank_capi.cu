@@ -99,7 +99,9 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_state) cudaFree(fb->d_state);
     if (fb->d_xh) cudaFree(fb->d_xh);
     fb->in_stage.release(); fb->out_stage.release(); fb->bands_stage.release(); fb->partial.release();
-    fb->scan_a.release(); fb->scan_b.release();
+    fb->scan_a.release(); fb->scan_b.release(); fb->env_stage.release();
+    if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);
+    if (fb->d_rms_ring) cudaFree(fb->d_rms_ring);
     delete fb;
     return HG_OK;
 }
@@ -227,6 +229,49 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     if (out_sum && !out_dev) { HG_CUDA(cudaMemcpyAsync(out_sum, d_out, S * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
     if (out_bands && !bands_dev) { HG_CUDA(cudaMemcpyAsync(out_bands, d_bands, S * N * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
     if (need_sync) HG_CUDA(cudaStreamSynchronize(st));
+    return HG_OK;
+}
+
+hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_env, size_t L, int width, int hop,
+                            void* cuda_stream) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process_env: null handle");
+    if (width < 64) return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process_env: width %d < 64 is not built (the fused follower fetches two 32-sample tiles of delayed values ahead)", width);
+    if (hop < 1) return hg::fail(HG_ERR_INVALID, "hg_fb_process_env: hop must be >= 1");
+    if (fb->rms_width && fb->rms_width != width)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_process_env: width %d differs from the handle's follower width %d", width, fb->rms_width);
+    if (L == 0) return HG_OK;
+    if (!out_sum) return hg::fail(HG_ERR_INVALID, "hg_fb_process_env: out_sum is required");
+    HG_CUDA(cudaSetDevice(fb->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t es = hg::dtype_size(fb->dtype), S = fb->S, N = fb->N;
+    if (!fb->d_rms_sum) {
+        // RMSbank(width) per (stream, filter): running sums and the ring of the last `width` squares, zeroed (rmsbank.h:34-44)
+        cudaError_t ce;
+        if ((ce = cudaMalloc(&fb->d_rms_sum, S * N * es)) != cudaSuccess ||
+            (ce = cudaMalloc(&fb->d_rms_ring, S * (size_t)width * ((N + 31) / 32 * 32) * es)) != cudaSuccess)
+            return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower state (%zu bytes): %s", S * (size_t)width * N * es, cudaGetErrorString(ce));
+        HG_CUDA(cudaMemsetAsync(fb->d_rms_sum, 0, S * N * es, st));
+        HG_CUDA(cudaMemsetAsync(fb->d_rms_ring, 0, S * (size_t)width * ((N + 31) / 32 * 32) * es, st));
+        fb->rms_width = width;
+        fb->rms_ticks = 0;
+    }
+    const size_t rows = L / (size_t)hop;
+    void* d_env = out_env;
+    const bool env_dev = out_env ? hg::is_device_ptr(out_env) : true;
+    if (out_env && !env_dev) { HG_TRY(fb->env_stage.reserve(S * rows * N * es)); d_env = fb->env_stage.p; }
+    fb->cur_env = d_env ? d_env : (void*)1;       // non-null marks "followers on" even without an envelope output
+    fb->cur_env_out = d_env;
+    fb->cur_hop = hop;
+    fb->cur_env_rows = rows;
+    hg_status rc = hg_fb_process(fb, in, out_sum, nullptr, L, HG_MODE_EXACT, HG_DIST_NONE, cuda_stream);
+    fb->cur_env = nullptr;
+    fb->cur_env_out = nullptr;
+    HG_TRY(rc);
+    fb->rms_ticks += (long long)L;
+    if (out_env && !env_dev) {
+        HG_CUDA(cudaMemcpyAsync(out_env, d_env, S * rows * N * es, cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaStreamSynchronize(st));
+    }
     return HG_OK;
 }
 

@@ -27,7 +27,17 @@ struct hg_fb {
     int force_cluster = -1;   // HG_FB_CLUSTER: cluster size of the ws kernel (1 disables), -1 = automatic
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
-    int ws_level = 0;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
+    int ws_level = 0;
+    // fused per-band envelope followers (hg_fb_process_env)
+    void* d_rms_sum = nullptr;   // [S][N]
+    void* d_rms_ring = nullptr;  // [S][ceil(N/32)][width][32]
+    int rms_width = 0;
+    long long rms_ticks = 0;
+    void* cur_env = nullptr;     // non-null while hg_fb_process_env runs (followers on)
+    void* cur_env_out = nullptr; // device pointer of the block's envelope output, may be null
+    int cur_hop = 0;
+    size_t cur_env_rows = 0;
+    hg::DevBuf env_stage;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
 };
 
 namespace hg {
@@ -56,8 +66,15 @@ template <typename T>
 hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, int level, const FbK1Params<T>& P, int groups, cudaStream_t st);
 template <typename T>
 int fb_ws_cluster_size(int groups, int streams, int level);
+template <typename T> struct FbEnvArgs {
+    T* env; T* rms_sum; T* rms_ring;
+    int width, hop;
+    long env_rows, t_base;
+    long long tick0;
+};
 template <typename T>
-hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st);
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st,
+                             const FbEnvArgs<T>* env = nullptr);
 template <typename T>
 void fb_ru_config(const hg_fb* fb, int* W_out, int* ctas_per_stream_out);
 template <typename T>

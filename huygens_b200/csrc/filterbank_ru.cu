@@ -25,6 +25,7 @@ constexpr int NB = 2;         // tile ring depth per RU warp
 constexpr int XT = 1024;      // input chunk
 constexpr int XB = 2;         // input ring depth
 constexpr int W_MAX = 14;     // RU warps per CTA
+constexpr int W_MAX_ENV = 8;  // ... with fused envelope followers: fewer warps, so the 32 prefetched ring values stay in registers
 constexpr int GPS = 2;        // RU warps served by one S warp: an S warp must not need more than its fair share
                               // of its scheduler's issue slots, or the RU warps starve behind it
 constexpr int NS_MAX = (W_MAX + GPS - 1) / GPS;
@@ -144,10 +145,20 @@ template <typename T> struct FbRuParams {
     FbK1Params<T> k;
     int W;            // RU warps per CTA
     int cps;          // CTAs per stream = ceil(ceil(N/32) / W)
+    // ENV variant: per-band RMSbank envelope followers fused behind the filters (src/rmsbank.h:54-74 on
+    // the real band outputs: q = y^2, S <- (q - q[t-width]) + S, env = sqrt(S / width))
+    T* env;               // [S][env_rows][N], one row every `hop` samples (row j = sample (j+1)*hop - 1 of the block)
+    T* rms_sum;           // [S][N] running sums
+    T* rms_ring;          // [S][ceil(N/32)][width][32] last `width` values of y^2 (HBM / L2 resident)
+    int width, hop;
+    long env_rows;
+    long t_base;          // first sample of this launch within the block
+    long long tick0;      // ticks rendered before this block (ring position)
 };
 
-template <typename T, bool FMA, bool BANDS>
-__global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_kernel(FbRuParams<T> Q) {
+template <typename T, bool FMA, bool BANDS, bool ENV>
+__global__ void __launch_bounds__(ENV ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV)) * 32 : (ru::W_MAX + ru::NS_MAX) * 32, 1)
+fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
     constexpr int RS = RowStride<T>::RS;
@@ -213,12 +224,34 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_
         int xb = 0, yb = 0, kc = 0;
         unsigned xpar = 0, ypar = 0;
         T t2 = A::mul(a2, y2);
+        // ENV: envelope follower state of this lane
+        T rsum = (ENV && ok) ? Q.rms_sum[si] : (T)0;
+        const T wT = (T)Q.width;
+        // ring layout [S][filter group of 32][width][32]: a warp's consecutive positions are consecutive 128-byte
+        // lines, so a tile of 32 samples is one contiguous 4 KB burst (DRAM-row friendly)
+        T* ring = ENV ? Q.rms_ring + (((size_t)s * groups + (w_first + warp)) * Q.width) * 32 + lane : nullptr;
+        int rpos = ENV ? (int)((Q.tick0 + Q.t_base) % Q.width) : 0;
+        long hop_left = ENV ? (long)Q.hop - (Q.t_base % Q.hop) : 0;        // samples until the next envelope row
+        long env_row = ENV ? Q.t_base / Q.hop : 0;
+        // ENV: the delayed squares q[t-width] live in one register buffer that is refilled in place: as soon as
+        // slot j of tile k has been consumed, slot j of tile k+1 is requested, so every ring load has a whole
+        // tile of arithmetic to land (width >= 2 * TILE keeps the two tiles' positions apart)
+        T qo[ENV ? TILE : 1];
+        if (ENV && ok) {
+            const int cnt0 = (ntiles == 1) ? last_tn : TILE;
+#pragma unroll
+            for (int j = 0; j < (ENV ? TILE : 1); j++) {
+                int pj = rpos + j;
+                if (pj >= Q.width) pj -= Q.width;
+                qo[j] = (j < cnt0) ? ring[(size_t)pj * 32] : (T)0;
+            }
+        }
         for (int k = 0; k < ntiles; k++) {
+            const int tn = (k == ntiles - 1) ? last_tn : TILE;
             if (kc == 0) mbar_wait(&x_full[xb], xpar);
             mbar_wait(&ye[yb], ypar ^ 1u);
             const T* xc = xs + xb * XT + kc * TILE;
             T* yrow = ybase + yb * 32 * RS;
-            const int tn = (k == ntiles - 1) ? last_tn : TILE;
             int tt = 0;
             if (conv && tn == TILE) {
                 // whole tile unrolled; `taps` is uniform, so pick the specialised body once per tile
@@ -250,6 +283,56 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_
             }
             if (!conv || tn != TILE) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
             if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            if (ENV && ok) {
+                // envelope follower over the tile just rendered (own row of the y tile), rmsbank.h:58-64
+                const int tn_next = (k + 1 >= ntiles) ? 0 : ((k + 1 == ntiles - 1) ? last_tn : TILE);
+                if (tn == TILE && tn_next == TILE && rpos + 2 * TILE <= Q.width && Q.hop >= TILE) {
+                    // fast path: full tile, full next tile, no ring wrap, at most one envelope row due: every ring
+                    // access is base + immediate offset
+                    const int je = hop_left <= TILE ? (int)hop_left - 1 : -1;
+                    T* base = ring + (size_t)rpos * 32;
+#pragma unroll
+                    for (int g4 = 0; g4 < TILE / 4; g4++) {
+                        T yv[4];
+                        ld4<T>(yrow + 4 * g4, yv);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int j = 4 * g4 + i;
+                            const T q = A::muladd((T)0, (T)0, A::mul(yv[i], yv[i]));
+                            rsum = A::add(A::sub(q, qo[j]), rsum);
+                            base[j * 32] = q;
+                            qo[j] = base[(TILE + j) * 32];
+                            if (j == je && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(rsum, wT));   // :64
+                        }
+                    }
+                    if (je >= 0) { env_row++; hop_left += Q.hop; }
+                    hop_left -= TILE;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TILE; j++) {
+                        int pj = rpos + j;
+                        if (pj >= Q.width) pj -= Q.width;
+                        if (j < tn) {
+                            const T y = yrow[j];
+                            const T q = A::muladd((T)0, (T)0, A::mul(y, y));       // |z|^2 of a real sample: y*y + 0*0
+                            rsum = A::add(A::sub(q, qo[j]), rsum);                 // (new - old) + last, :60
+                            ring[(size_t)pj * 32] = q;
+                            if (--hop_left == 0) {
+                                if (Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(rsum, wT));   // :64
+                                env_row++;
+                                hop_left = Q.hop;
+                            }
+                        }
+                        if (j < tn_next) {                                         // refill slot j for the next tile
+                            int pn = pj + TILE;
+                            if (pn >= Q.width) pn -= Q.width;
+                            qo[j] = ring[(size_t)pn * 32];
+                        }
+                    }
+                }
+                rpos += tn;
+                if (rpos >= Q.width) rpos -= Q.width;
+            }
             __syncwarp();
             const bool chunk_done = (kc == TPC - 1) || (k == ntiles - 1);
             if (lane == 0) {
@@ -259,7 +342,10 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_
             if (++yb == NB) { yb = 0; ypar ^= 1u; }
             if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
         }
-        if (ok) { P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[2 * SN + si] = p; }
+        if (ok) {
+            P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[2 * SN + si] = p;
+            if (ENV) Q.rms_sum[si] = rsum;
+        }
         if (cta == 0 && warp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
     } else {
         // ------------------------------ S: mixdown, gains, input ring ------------------------------
@@ -402,11 +488,12 @@ __global__ void __launch_bounds__((ru::W_MAX + ru::NS_MAX) * 32, 1) fb_exact_ru_
 template <typename T>
 void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
     const int groups = (fb->N + 31) / 32;
+    const int w_max = fb->cur_env ? ru::W_MAX_ENV : ru::W_MAX;
     const size_t smem_sm = (size_t)227 * 1024;
     int bestW = 4;
     double best = -1;
     for (int per_sm = 1; per_sm <= 2; per_sm++) {
-        for (int W = 4; W <= ru::W_MAX; W++) {
+        for (int W = 4; W <= w_max; W++) {
             if ((ru::Layout<T>(W).bytes() + 1024) * per_sm > smem_sm) continue;
             const long slots = (long)fb->sm_count * per_sm;
             const long ctas = (long)((groups + W - 1) / W) * fb->S;
@@ -425,24 +512,31 @@ void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
 template void fb_ru_config<float>(const hg_fb*, int*, int*);
 template void fb_ru_config<double>(const hg_fb*, int*, int*);
 
-template <typename T, bool FMA, bool BANDS>
-static hg_status launch_ru(const FbK1Params<T>& P, int W, int cps, cudaStream_t st) {
-    FbRuParams<T> Q;
-    Q.k = P; Q.W = W; Q.cps = cps;
-    const size_t smem = ru::Layout<T>(W).bytes();
-    auto kern = fb_exact_ru_kernel<T, FMA, BANDS>;
+template <typename T, bool FMA, bool BANDS, bool ENV>
+static hg_status launch_ru(const FbRuParams<T>& Q, cudaStream_t st) {
+    const size_t smem = ru::Layout<T>(Q.W).bytes();
+    auto kern = fb_exact_ru_kernel<T, FMA, BANDS, ENV>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(cps, P.S), (W + ru::s_warps(W)) * 32, smem, st>>>(Q);
+    kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W)) * 32, smem, st>>>(Q);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
 
 template <typename T>
-hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int cps, cudaStream_t st) {
-    if (bands) return fma ? launch_ru<T, true, true>(P, W, cps, st) : launch_ru<T, false, true>(P, W, cps, st);
-    return fma ? launch_ru<T, true, false>(P, W, cps, st) : launch_ru<T, false, false>(P, W, cps, st);
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int cps, cudaStream_t st, const FbEnvArgs<T>* env) {
+    FbRuParams<T> Q;
+    Q.k = P; Q.W = W; Q.cps = cps;
+    Q.env = nullptr; Q.rms_sum = nullptr; Q.rms_ring = nullptr; Q.width = 1; Q.hop = 1; Q.env_rows = 0; Q.t_base = 0; Q.tick0 = 0;
+    if (env) {
+        Q.env = env->env; Q.rms_sum = env->rms_sum; Q.rms_ring = env->rms_ring; Q.width = env->width; Q.hop = env->hop;
+        Q.env_rows = env->env_rows; Q.t_base = env->t_base; Q.tick0 = env->tick0;
+        if (bands) return fail(HG_ERR_UNSUPPORTED, "envelope followers and per-band outputs cannot be combined");
+        return fma ? launch_ru<T, true, false, true>(Q, st) : launch_ru<T, false, false, true>(Q, st);
+    }
+    if (bands) return fma ? launch_ru<T, true, true, false>(Q, st) : launch_ru<T, false, true, false>(Q, st);
+    return fma ? launch_ru<T, true, false, false>(Q, st) : launch_ru<T, false, false, false>(Q, st);
 }
-template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, cudaStream_t);
-template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, cudaStream_t);
+template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, cudaStream_t, const FbEnvArgs<float>*);
+template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, cudaStream_t, const FbEnvArgs<double>*);
 
 }  // namespace hg

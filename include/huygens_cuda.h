@@ -84,6 +84,14 @@ hg_status hg_fb_open(hg_fb* fb);
  * distortion != NONE selects operator()(sample, distortion) :133-139. */
 hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_bands, size_t L,
                         int mode, int distortion, void* cuda_stream);
+/* new: the same block render with one RMSbank<T,.>(width) envelope follower per (stream, filter) fused
+ * behind the filters (src/rmsbank.h:54-74 applied to the real band output y_n: q = y^2,
+ * S <- (q - q[t-width]) + S, env = sqrt(S/width)); BASELINE configs[3].  out_env (nullable)
+ * [n_streams][L/hop][n_filters] receives env at block samples hop-1, 2*hop-1, ...; the follower state
+ * (running sums and the ring of the last `width` squares) persists in the handle; width >= 64 and
+ * fixed at the first call.  Bit-identical to Filterbank bands -> RMSbank. */
+hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_env, size_t L, int width,
+                            int hop, void* cuda_stream);
 /* state access (streaming / checkpoint tests): y1,y2,p,g are [n_streams][n_filters]; xhist is
  * [n_streams][2] = x[t-1], x[t-2].  Host pointers. NULL entries are skipped. */
 hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void* xhist);
