@@ -284,14 +284,22 @@ def main():
 
     # end to end through the public API with host buffers (H2D + D2H inside the call)
     xh, oh = x_host.numpy(), out_host.numpy()
+    env_h = torch.empty(env_buf.shape, dtype=tdtype).pin_memory().numpy() if args.env else None
+
+    def render_host():
+        if args.env:
+            fb.process_env(xh, width=2400, hop=64, out=oh, env=env_h)   # envelopes come back to the host too
+        else:
+            fb.process(xh, out=oh, mode=args.mode)
+
     for _ in range(2):
-        fb.process(xh, out=oh, mode=args.mode)
+        render_host()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fb.process(xh, out=oh, mode=args.mode)       # synchronises before returning
+        render_host()                                # synchronises before returning
         if world > 1:
             # partial sums meet on rank 0: host -> device -> reduce would double count copies; the
             # device-side reduce of the staged output is what a sharded caller does
@@ -347,7 +355,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.get("dtype", "f32"), "data": "synthetic",
         "config": workload_config(w, args, world),
-        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * x_host.element_size()), "d2h_bytes_per_step": int(S * L * x_host.element_size())},
+        "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * x_host.element_size()), "d2h_bytes_per_step": int(S * L * x_host.element_size() + (env_h.nbytes if args.env else 0))},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
