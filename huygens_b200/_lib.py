@@ -46,6 +46,7 @@ SYMBOLS = [
     ("hg_osc_close", _i, [_vp]),
     ("hg_osc_active_count", _i, [_vp]),
     ("hg_osc_process", _i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    ("hg_osc_process_env", _i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp]),
     ("hg_osc_get_phases", _i, [_vp, _vp]),
     ("hg_osc_set_phases", _i, [_vp, _vp]),
     ("hg_rms_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),

@@ -226,8 +226,9 @@ class Oscbank(_Handle):
     def active_count(self):
         return L.lib().hg_osc_active_count(self._h)
 
-    def process(self, Ls, amps=None, want_mix=True, device_out=False):
-        """Ls ticks: mix[t] = mixdown() before tick t; amix[t] = sum_n amps[n] * Re(phase_n)."""
+    def process(self, Ls, amps=None, want_mix=True, device_out=False, hop=None):
+        """Ls ticks: mix[t] = mixdown() before tick t; amix[t] = sum_n amps[n] * Re(phase_n).
+        With hop, amps is [rows][N] and row r drives ticks [r*hop, (r+1)*hop) (hg_osc_process_env)."""
         cdt = np.complex64 if self.dtype == np.float32 else np.complex128
         if device_out:
             import torch
@@ -241,7 +242,10 @@ class Oscbank(_Handle):
         am = None
         if amps is not None:
             am = amps if _is_torch(amps) else np.ascontiguousarray(amps, dtype=self.dtype)
-        L.check(L.lib().hg_osc_process(self._h, _ptr(mix), _ptr(am), _ptr(amix), Ls, stream))
+        if hop is not None:
+            L.check(L.lib().hg_osc_process_env(self._h, _ptr(mix), _ptr(am), int(am.shape[0]), int(hop), _ptr(amix), Ls, stream))
+        else:
+            L.check(L.lib().hg_osc_process(self._h, _ptr(mix), _ptr(am), _ptr(amix), Ls, stream))
         res = [r for r in (mix, amix) if r is not None]
         return res[0] if len(res) == 1 else tuple(res)
 

@@ -120,6 +120,12 @@ int hg_osc_active_count(hg_osc* osc);
  * Any of out_mix / out_amix may be NULL; amps is [n_partials] and required iff out_amix. */
 hg_status hg_osc_process(hg_osc* osc, void* out_mix, const void* amps, void* out_amix, size_t L,
                          void* cuda_stream);
+/* The same, with time-varying amplitudes: row r of amp_rows [n_rows][n_partials] drives ticks
+ * [r*hop, (r+1)*hop) of this block — the resynthesis half of tests/resynthesis.cpp-style chains, where the
+ * amplitudes are the envelope rows of hg_fb_process_env / hg_rms_process (modbank.h:41-45 with a new
+ * amplitude vector every hop ticks).  n_rows * hop >= L; out_amix is required, out_mix optional. */
+hg_status hg_osc_process_env(hg_osc* osc, void* out_mix, const void* amp_rows, size_t n_rows, int hop,
+                             void* out_amix, size_t L, void* cuda_stream);
 hg_status hg_osc_get_phases(hg_osc* osc, void* phases /* complex interleaved [n_partials], host */);
 hg_status hg_osc_set_phases(hg_osc* osc, const void* phases);
 

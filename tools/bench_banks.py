@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--partials", type=int, default=65536)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--channels", type=int, default=1024)
+    ap.add_argument("--chain", action="store_true", help="also time the analysis -> resynthesis chain (BASELINE configs[4])")
     args = ap.parse_args()
     L = int(args.seconds * 48000)
     peak = hb.fma_peak(np.float32)["slots_per_s"]
@@ -55,6 +56,28 @@ def main():
         t = timed(lambda: rms.process(z))
         res[f"rmsbank_{np.dtype(dtype).name}"] = {"channels": C, "samples": Lr, "s": t, "channel_samples_per_s": C * Lr / t,
                                                   "hbm_GBps_algorithmic": C * Lr * 2 * z.element_size() / t / 1e9}
+    if args.chain:
+        # BASELINE configs[4]: N partials driven by Filterbank/RMSbank analysis of the same signal —
+        # Filterbank(N) + fused per-band followers (hop 64) -> envelope rows -> Oscbank(N) amplitudes
+        N, hop = args.partials, 64
+        freqs = design.log_spaced(N, 27.5, 20000.0)
+        fwd, back, gains = design.resonator_bank(freqs, 0.999)
+        fb = hb.Filterbank(2, N, k_p=0.001, k_g=1.0, dtype=np.float32)
+        fb.coefficients(0, fwd, back)
+        fb.boost(np.ones(N))
+        fb.mix(gains / N)
+        osc = hb.Oscbank(N, dtype=np.float32)
+        osc.set_frequencies(freqs)
+        osc.open()
+        x = torch.from_numpy(design.chirp(L, dtype=np.float32)).cuda()
+        out = torch.empty_like(x)
+        env = torch.empty((1, L // hop, N), dtype=torch.float32, device="cuda")
+        t_an = timed(lambda: fb.process_env(x, width=2400, hop=hop, out=out, env=env))
+        rows = env[0]
+        t_sy = timed(lambda: osc.process(rows.shape[0] * hop, amps=rows, hop=hop, want_mix=False, device_out=True))
+        res["resynthesis_chain_float32"] = {"partials": N, "samples": L, "hop": hop, "analysis_s": t_an, "synthesis_s": t_sy,
+                                            "partial_samples_per_s": N * L / (t_an + t_sy),
+                                            "analysis_hbm_GBps_algorithmic": N * L * 8 / t_an / 1e9}
     print(json.dumps(res))
 
 
