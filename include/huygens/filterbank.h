@@ -86,6 +86,12 @@ public:
     void process_bands(const T* in, T* bands, size_t L, T* out_sum = nullptr, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process(fb, in, out_sum, bands, L, HG_MODE_EXACT, HG_DIST_NONE, cuda_stream));
     }
+    // new: process() + one RMSbank(width) envelope follower per band (src/rmsbank.h:54-74 applied to every
+    // output of compute()), fused; env[(s * rows + r) * N + n] is the follower of band n after block sample
+    // (r+1)*hop - 1, rows = L / hop.  The follower state persists across calls like the filters' own.
+    void process_env(const T* in, T* out_sum, T* env, size_t L, int width = SR / 20, int hop = 64, void* cuda_stream = nullptr) {
+        hg_check(hg_fb_process_env(fb, in, out_sum, env, L, width, hop, cuda_stream));
+    }
     int size() const { return N; }
     hg_fb* handle() { return fb; }
 

@@ -44,6 +44,13 @@ public:
         hg_check(hg_osc_process(osc, mix, amps, amix, L, cuda_stream));
         fresh = false;
     }
+    // new: the same with one amplitude vector per `hop` ticks — amp_rows[r * N + n] drives ticks [r*hop, (r+1)*hop)
+    // (envelope rows of Filterbank::process_env as Modbank amplitudes, src/modbank.h:41-45)
+    void process_env(const T* amp_rows, size_t n_rows, int hop, T* amix, size_t L, std::complex<T>* mix = nullptr,
+                     void* cuda_stream = nullptr) {
+        hg_check(hg_osc_process_env(osc, mix, amp_rows, n_rows, hop, amix, L, cuda_stream));
+        fresh = false;
+    }
     hg_osc* handle() { return osc; }
 
 protected:
