@@ -5,6 +5,8 @@
 #include "../include/huygens/oscbank.h"
 #include "../include/huygens/rmsbank.h"
 #include "../include/huygens/latchbank.h"
+#include "../include/huygens/slidebank.h"
+#include "../include/huygens/stickbank.h"
 
 using namespace soundmath;
 
@@ -18,6 +20,11 @@ int main(int argc, char** argv) {
         RMSbank<double, 8> rms2(16);
         Latchbank<double, 8> latch(0.9, 0.2);        // tests/rmsbank.cpp:15
         FFilterbank<double, 4, 2> F(0.001, 1);
+        // tests/slidebank.cpp:52-56,92-101: heterodyned phasors -> Slidebank low-passes -> Stickbank smoother
+        std::vector<std::complex<double>> radii;
+        for (int i = 0; i < 8; i++) radii.push_back(std::complex<double>(0.99 - 0.01 * i, 0.002 * i));
+        Slidebank<double, 8> slide(2, radii);
+        Stickbank<double, 8> smooth(1, -0.9);
         for (int i = 0; i < 8; i++) osc.freqmod(i, 110.0 * (i + 1));
         osc.freqmod(99, 1.0);       // ignored, oscbank.h:51
         osc.open();
@@ -36,8 +43,12 @@ int main(int argc, char** argv) {
             const auto* gated = latch(&rms2, ph);               // tests/harmbank.cpp:84-86
             double gsum = 0;
             for (int i = 0; i < 8; i++) gsum += (*gated)(i).real();
-            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum);
-            osc.tick(); rms.tick(); rms2.tick(); F.tick();
+            const auto* sm = smooth(slide(ph));
+            std::complex<double> ssum = 0;
+            for (int i = 0; i < 8; i++) ssum += (*sm)(i);
+            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum,
+                        ssum.real(), ssum.imag());
+            osc.tick(); rms.tick(); rms2.tick(); F.tick(); slide.tick(); smooth.tick();
         }
     } catch (const cuda_error& e) {
         std::fprintf(stderr, "huygens_cuda error %d: %s\n", e.status, e.what());

@@ -54,6 +54,11 @@ SYMBOLS = [
     ("hg_rms_process", _i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     ("hg_rms_set_latch", _i, [_vp, _d, _d]),
     ("hg_rms_process_latch", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    ("hg_slide_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _vp, _i]),
+    ("hg_stick_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _d, _i]),
+    ("hg_stick_rmod", _i, [_vp, _d]),
+    ("hg_casc_destroy", _i, [_vp]),
+    ("hg_casc_process", _i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 ]
 
 

@@ -307,6 +307,46 @@ class Latchbank:
         return res[0] if len(res) == 1 else tuple(res)
 
 
+class _Cascade(_Handle):
+    _destroy = "hg_casc_destroy"
+
+    def process(self, z):
+        """z [N][L] (complex or real) -> complex [N][L]: L ticks of `out = bank(&z); bank.tick()`."""
+        z = np.asarray(z)
+        Ls = z.shape[1]
+        zre = np.ascontiguousarray(z.real, dtype=self.dtype)
+        zim = np.ascontiguousarray(z.imag, dtype=self.dtype) if np.iscomplexobj(z) else None
+        ore, oim = np.empty((self.N, Ls), self.dtype), np.empty((self.N, Ls), self.dtype)
+        L.check(L.lib().hg_casc_process(self._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), Ls, None))
+        out = np.empty((self.N, Ls), np.complex64 if self.dtype == np.float32 else np.complex128)
+        out.real, out.imag = ore, oim
+        return out
+
+
+class Slidebank(_Cascade):
+    """Slidebank<T,N>(order, radii) — src/slidebank.h:19-186."""
+
+    def __init__(self, N, order, radii, dtype=np.float64, arith="strict", device=0):
+        super().__init__(dtype, arith)
+        self.N, self.order = N, max(1, order)
+        r = np.ascontiguousarray(np.asarray(radii, dtype=np.complex128))
+        if r.shape != (N,):
+            raise ValueError("radii must hold one complex radius per channel")
+        L.check(L.lib().hg_slide_create(C.byref(self._h), self.hg_dtype, self.arith, N, order, _ptr(r.view(np.float64)), device))
+
+
+class Stickbank(_Cascade):
+    """Stickbank<T,N>(order, rad) — src/stickbank.h:15-221."""
+
+    def __init__(self, N, order, rad, dtype=np.float64, arith="strict", device=0):
+        super().__init__(dtype, arith)
+        self.N, self.order = N, max(1, order)
+        L.check(L.lib().hg_stick_create(C.byref(self._h), self.hg_dtype, self.arith, N, order, float(rad), device))
+
+    def rmod(self, rad):
+        L.check(L.lib().hg_stick_rmod(self._h, float(rad)))
+
+
 def fma_peak(dtype=np.float32, device=0):
     """Measured FMA issue rate (lane-FMA slots/s), SM count and SM clock (MHz) of `device`."""
     s, n, m = C.c_double(), C.c_int(), C.c_double()

@@ -45,6 +45,7 @@ enum { HG_DIST_NONE = 0, HG_DIST_SOFTCLIP = 1 /* tests/filterbank.cpp:158-171, w
 
 typedef struct hg_fb hg_fb;
 typedef struct hg_osc hg_osc;
+typedef struct hg_casc hg_casc;
 typedef struct hg_rms hg_rms;
 
 const char* hg_last_error(void);
@@ -145,6 +146,20 @@ hg_status hg_rms_set_latch(hg_rms* rms, double thresh, double ratio);
  * zim / out_im may both be NULL (real signal). */
 hg_status hg_rms_process_latch(hg_rms* rms, const void* zre, const void* zim, void* out_re, void* out_im,
                                void* out_level, size_t L, void* cuda_stream);
+
+/* ---- Slidebank<T,N> / Stickbank<T,N>  (src/slidebank.h, src/stickbank.h) ---------------------- */
+/* Slidebank(order, radii) slidebank.h:53-97: per channel a cascade of max(1, order) complex one-pole
+ * low-passes with radius radii[n] (complex interleaved [n_channels]), one tick of delay per stage.
+ * Stickbank(order, rad) stickbank.h:46-78: every channel through the all-pole smoother with max(1, order)
+ * poles from coefficients() (:198-218); rmod (:69-79) re-derives them.  order <= 16. */
+hg_status hg_slide_create(hg_casc** out, int dtype, int arith, int n_channels, int order, const double* radii, int device);
+hg_status hg_stick_create(hg_casc** out, int dtype, int arith, int n_channels, int order, double rad, int device);
+hg_status hg_stick_rmod(hg_casc* bank, double rad);
+hg_status hg_casc_destroy(hg_casc* bank);
+/* L ticks of `out = bank(&z); bank.tick();` (slidebank.h:100-124,166-175; stickbank.h:82-107,181-195).
+ * zre, zim, out_re, out_im: [n_channels][L] channel-major; zim may be NULL (real input, :111-117 / :91-98). */
+hg_status hg_casc_process(hg_casc* bank, const void* zre, const void* zim, void* out_re, void* out_im, size_t L,
+                          void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,13 @@ def lib():
             f("hgo_latch_destroy").argtypes = [C.c_void_p]
             f("hgo_latch_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
             f("hgo_latch_process_real").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+            f("hgo_slide_create").restype = C.c_void_p
+            f("hgo_slide_create").argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            f("hgo_stick_create").restype = C.c_void_p
+            f("hgo_stick_create").argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+            f("hgo_casc_destroy").argtypes = [C.c_void_p]
+            f("hgo_casc_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+            f("hgo_stick_rmod").argtypes = [C.c_void_p, C.c_double]
     return _LIB
 
 
@@ -218,6 +225,49 @@ class RMSbank(_Base):
         return out
 
 
+class _Cascade(_Base):
+    """Shared block driver of Slidebank / Stickbank: complex channel-major input z[N][L] -> output [N][L]."""
+
+    def __del__(self):
+        if self._h:
+            self._f("hgo_casc_destroy")(self._h)
+            self._h = None
+
+    def process(self, z):
+        z = np.asarray(z)
+        L = z.shape[1]
+        assert z.shape[0] == self.N
+        zre = np.ascontiguousarray(z.real, dtype=self.dtype)
+        zim = np.ascontiguousarray(z.imag, dtype=self.dtype) if np.iscomplexobj(z) else None
+        ore, oim = np.empty((self.N, L), self.dtype), np.empty((self.N, L), self.dtype)
+        self._f("hgo_casc_process")(self._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), L)
+        return ore + 1j * oim if self.dtype == np.float64 else (ore + 1j * oim).astype(np.complex64)
+
+
+class Slidebank(_Cascade):
+    """Slidebank<T,N>(order, radii) — slidebank.h:19-186: cascades of complex one-pole low-passes."""
+
+    def __init__(self, N, order, radii, dtype=np.float64, mode="strict"):
+        super().__init__(dtype, mode)
+        self.N, self.order = N, max(1, order)
+        r = np.asarray(radii, dtype=np.complex128)
+        assert r.shape == (N,)
+        rr, ri = np.ascontiguousarray(r.real), np.ascontiguousarray(r.imag)
+        self._h = self._f("hgo_slide_create")(DTYPES[self.dtype], N, order, _ptr(rr), _ptr(ri))
+
+
+class Stickbank(_Cascade):
+    """Stickbank<T,N>(order, rad) — stickbank.h:15-221: N channels through one all-pole smoother."""
+
+    def __init__(self, N, order, rad, dtype=np.float64, mode="strict"):
+        super().__init__(dtype, mode)
+        self.N, self.order = N, max(1, order)
+        self._h = self._f("hgo_stick_create")(DTYPES[self.dtype], N, order, float(rad))
+
+    def rmod(self, rad):
+        self._f("hgo_stick_rmod")(self._h, float(rad))
+
+
 class Latchbank(_Base):
     """Latchbank<T,N>(thresh, ratio) gating an RMSbank<T,N>(width) — latchbank.h:16-105.
     process(): per tick gated = latch(&rms, z); rms.tick().  process_real(): out = latch(level)."""
@@ -288,6 +338,9 @@ def ref_lib():
             "hgr_latch_create": (vp, [i, i, i, d, d]), "hgr_latch_destroy": (None, [vp]),
             "hgr_latch_process": (None, [vp, vp, vp, vp, vp, vp, lg]),
             "hgr_latch_process_real": (None, [vp, vp, vp, lg]),
+            "hgr_slide_create": (vp, [i, i, i, vp, vp]), "hgr_stick_create": (vp, [i, i, i, d]),
+            "hgr_casc_destroy": (None, [vp]), "hgr_casc_process": (None, [vp, vp, vp, vp, vp, lg]),
+            "hgr_stick_rmod": (None, [vp, d]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(_REF, name)
@@ -437,3 +490,47 @@ class RefLatchbank:
         out = np.empty_like(x)
         ref_lib().hgr_latch_process_real(self._h, _ptr(x), _ptr(out), x.shape[1])
         return out
+
+
+REF_CASC_N = (1, 8, 96)
+
+
+class _RefCascade:
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().hgr_casc_destroy(self._h)
+            self._h = None
+
+    def process(self, z):
+        z = np.asarray(z)
+        L = z.shape[1]
+        zre = np.ascontiguousarray(z.real, dtype=self.dtype)
+        zim = np.ascontiguousarray(z.imag, dtype=self.dtype) if np.iscomplexobj(z) else None
+        ore, oim = np.empty((self.N, L), self.dtype), np.empty((self.N, L), self.dtype)
+        ref_lib().hgr_casc_process(self._h, _ptr(zre), _ptr(zim), _ptr(ore), _ptr(oim), L)
+        return ore + 1j * oim if self.dtype == np.float64 else (ore + 1j * oim).astype(np.complex64)
+
+
+class RefSlidebank(_RefCascade):
+    """soundmath::Slidebank<T,N>(order, radii), N in REF_CASC_N."""
+
+    def __init__(self, N, order, radii, dtype=np.float64):
+        self.dtype, self.N = np.dtype(dtype), N
+        r = np.asarray(radii, dtype=np.complex128)
+        rr, ri = np.ascontiguousarray(r.real), np.ascontiguousarray(r.imag)
+        self._h = ref_lib().hgr_slide_create(DTYPES[self.dtype], N, order, _ptr(rr), _ptr(ri))
+        if not self._h:
+            raise ValueError("this Slidebank<T,N> is not instantiated in ref_capi.cpp")
+
+
+class RefStickbank(_RefCascade):
+    """soundmath::Stickbank<double,N>(order, rad), N in REF_CASC_N (the template only compiles for double)."""
+
+    def __init__(self, N, order, rad, dtype=np.float64):
+        self.dtype, self.N = np.dtype(dtype), N
+        self._h = ref_lib().hgr_stick_create(DTYPES[self.dtype], N, order, float(rad))
+        if not self._h:
+            raise ValueError("this Stickbank<T,N> is not instantiated in ref_capi.cpp")
+
+    def rmod(self, rad):
+        ref_lib().hgr_stick_rmod(self._h, float(rad))

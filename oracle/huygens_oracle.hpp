@@ -341,4 +341,103 @@ private:
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Complex products as g++ -O3 evaluates std::complex<T> operator* on finite values:
+// (a+ib)(c+id) = (ac - bd) + i(ad + bc); the fma mode contracts like Oscbank::tick above.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> inline void cmul(T a, T b, T c, T d, T& re, T& im) {
+    if (FMA) { re = std::fma(-b, d, a * c); im = std::fma(b, c, a * d); }
+    else { T ac = a * c, bd = b * d, ad = a * d, bc = b * c; re = ac - bd; im = ad + bc; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slidebank<T,N>  (src/slidebank.h:19-186): per channel a cascade of `order` complex one-pole
+// low-passes sharing one radius r, written in the reference as ONE sparse matrix `back` applied to
+// the stacked vector [input ; states]: every stage reads the PREVIOUS tick's value of the stage
+// before it (one tick of delay per stage).  Row (i + j*order) holds (1-r_j) at the column of its
+// source and r_j at the column of its own state (:71-83); Eigen's column-major sparse x dense
+// product visits columns in ascending order and does  res += value * (alpha * rhs_j), alpha = 1:
+//   s_i' = (0 + (1-r) * (1*src)) + r * (1*s_i),   src = input (i = 0) or s_{i-1};   out = s_{order-1}'
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class Slidebank : public Multichannel {
+public:
+    Slidebank(int N, int order, const T* rad_re, const T* rad_im)                       // :53-97 setup()
+        : Multichannel(N), order(std::max(1, order)), rr(rad_re, rad_re + N), ri(rad_im, rad_im + N),
+          qr(N), qi(N), sr((size_t)N * this->order, 0), si((size_t)N * this->order, 0), nr(this->order), ni(this->order) {
+        for (int j = 0; j < N; j++) { qr[j] = (T)1 - rr[j]; qi[j] = (T)0 - ri[j]; }      // complex(1,0) - radii[j]
+    }
+    // :100-106 + :166-175   one tick: input x (complex), output = last stage, all channels
+    void operator()(const T* xre, const T* xim, T* ore, T* oim) {
+        for (int j = 0; j < N; j++) {
+            T* s_r = &sr[(size_t)j * order]; T* s_i = &si[(size_t)j * order];
+            for (int i = 0; i < order; i++) {
+                const T ar = i == 0 ? xre[j] : s_r[i - 1], ai = i == 0 ? (xim ? xim[j] : (T)0) : s_i[i - 1];
+                T ur, ui, vr, vi, pr, pi, wr, wi;
+                cmul<T, FMA>((T)1, (T)0, ar, ai, ur, ui);               // alpha * rhs(source column)
+                cmul<T, FMA>(qr[j], qi[j], ur, ui, pr, pi);             // (1 - r) * ...
+                T acc_r = (T)0 + pr, acc_i = (T)0 + pi;
+                cmul<T, FMA>((T)1, (T)0, s_r[i], s_i[i], vr, vi);       // alpha * rhs(own column)
+                cmul<T, FMA>(rr[j], ri[j], vr, vi, wr, wi);             // r * ...
+                nr[i] = acc_r + wr; ni[i] = acc_i + wi;
+            }
+            for (int i = 0; i < order; i++) { s_r[i] = nr[i]; s_i[i] = ni[i]; }
+            ore[j] = s_r[order - 1]; oim[j] = s_i[order - 1];
+        }
+    }
+    int order;
+    std::vector<T> rr, ri, qr, qi, sr, si;
+private:
+    std::vector<T> nr, ni;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stickbank<T,N>  (src/stickbank.h:15-221): N channels through the same all-pole filter whose
+// denominator has `order` roots at `rad`:  y[t] = (1+rad)^order x[t] - sum_k back[k] y[t-1-k]
+// (:181-195); back = the low `order` coefficients of prod (z + rad) from the recursive
+// coefficients() (:198-218).  The N x order complex GEMV adds its columns one after the other from
+// zero (our reading of Eigen's order for order > 1; every caller in the reference uses order 1).
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA> class Stickbank : public Multichannel {
+public:
+    Stickbank(int N, int order, T rad) : Multichannel(N), order(std::max(1, order)), yr((size_t)N * this->order, 0),
+                                         yi((size_t)N * this->order, 0) { rmod(rad); }
+    void rmod(T rad_) {                                                                  // :47-58, :69-79
+        rad = rad_;
+        std::vector<T> zeros(order, rad);
+        std::vector<T> c = coefficients(zeros, 0);
+        back.assign(c.begin(), c.begin() + order);
+        scale = (T)std::pow((double)((T)1 + rad), order);
+    }
+    void operator()(const T* xre, const T* xim, T* ore, T* oim) {                         // :82-89 + :181-195
+        for (int j = 0; j < N; j++) {
+            T* h_r = &yr[(size_t)j * order]; T* h_i = &yi[(size_t)j * order];            // h[k] = y[t-1-k]
+            T acc_r = 0, acc_i = 0;
+            for (int k = 0; k < order; k++) {
+                T pr, pi;
+                cmul<T, FMA>(h_r[k], h_i[k], back[k], (T)0, pr, pi);
+                acc_r = acc_r + pr; acc_i = acc_i + pi;
+            }
+            const T xi = xim ? xim[j] : (T)0;
+            const T tr = scale * xre[j] - acc_r, ti = scale * xi - acc_i;
+            for (int k = order - 1; k > 0; k--) { h_r[k] = h_r[k - 1]; h_i[k] = h_i[k - 1]; }
+            h_r[0] = tr; h_i[0] = ti;
+            ore[j] = tr; oim[j] = ti;
+        }
+    }
+    // :198-218  coefficients of the monic polynomial with the given roots' negatives, lowest degree first
+    static std::vector<T> coefficients(const std::vector<T>& zeros, int start) {
+        const int degree = (int)zeros.size() - start;
+        if (degree == 0) return {0};
+        if (degree == 1) return {zeros[start], 1};
+        std::vector<T> total(degree + 1, 0);
+        const T first = zeros[start];
+        std::vector<T> shifted(coefficients(zeros, start + 1));
+        for (int i = 0; i < degree; i++) { total[i] += first * shifted[i]; total[i + 1] += shifted[i]; }
+        return total;
+    }
+    int order;
+    T rad, scale;
+    std::vector<T> back, yr, yi;
+};
+
 }  // namespace hgoracle

@@ -22,6 +22,8 @@
 #include HG_STR(HG_REF_SRC/oscbank.h)
 #include HG_STR(HG_REF_SRC/rmsbank.h)
 #include HG_STR(HG_REF_SRC/latchbank.h)
+#include HG_STR(HG_REF_SRC/slidebank.h)
+#include HG_STR(HG_REF_SRC/stickbank.h)
 #undef private
 #undef protected
 
@@ -208,6 +210,57 @@ template <typename T> RmsBase* make_rms(int N, int width) {
     return nullptr;
 }
 
+// Slidebank<T,N> / Stickbank<T,N> (src/slidebank.h, src/stickbank.h), driven tick by tick like
+// tests/slidebank.cpp:92-101: out = bank(&z); bank.tick().  Complex channel-major blocks [N][L].
+struct CascBase {
+    virtual ~CascBase() {}
+    virtual void process(const void* xre, const void* xim, void* ore, void* oim, long L) = 0;
+    virtual void rmod(double) {}
+};
+template <typename T, int N, typename Bank> struct CascImpl : CascBase {
+    Bank* bank = nullptr;
+    ~CascImpl() { delete bank; }
+    void process(const void* xre_, const void* xim_, void* ore_, void* oim_, long L) override {
+        const T* xre = (const T*)xre_; const T* xim = (const T*)xim_; T* ore = (T*)ore_; T* oim = (T*)oim_;
+        Eigen::Array<std::complex<T>, Eigen::Dynamic, 1> z;
+        z.resize(N);
+        for (long t = 0; t < L; t++) {
+            for (int n = 0; n < N; n++) z(n) = std::complex<T>(xre[(size_t)n * L + t], xim ? xim[(size_t)n * L + t] : (T)0);
+            const auto* o = (*bank)(&z);
+            for (int n = 0; n < N; n++) { ore[(size_t)n * L + t] = (*o)(n).real(); oim[(size_t)n * L + t] = (*o)(n).imag(); }
+            bank->tick();
+        }
+    }
+};
+template <typename T, int N> CascBase* new_slide(int order, const double* rr, const double* ri) {
+    std::vector<std::complex<T>> radii(N);
+    for (int n = 0; n < N; n++) radii[n] = std::complex<T>((T)rr[n], (T)ri[n]);
+    auto* impl = new CascImpl<T, N, Slidebank<T, N>>();
+    impl->bank = new Slidebank<T, N>(order, radii);
+    return impl;
+}
+template <typename T> CascBase* make_slide(int N, int order, const double* rr, const double* ri) {
+    switch (N) {
+        case 1: return new_slide<T, 1>(order, rr, ri);
+        case 8: return new_slide<T, 8>(order, rr, ri);
+        case 96: return new_slide<T, 96>(order, rr, ri);
+    }
+    return nullptr;
+}
+// Stickbank compiles for T = double only (stickbank.h:49-50 hands a std::vector<double> to coefficients(const std::vector<T>&))
+template <int N> struct StickImpl : CascImpl<double, N, Stickbank<double, N>> {
+    StickImpl(int order, double rad) { this->bank = new Stickbank<double, N>(order, rad); }
+    void rmod(double r) override { this->bank->rmod(r); }
+};
+CascBase* make_stick(int N, int order, double rad) {
+    switch (N) {
+        case 1: return new StickImpl<1>(order, rad);
+        case 8: return new StickImpl<8>(order, rad);
+        case 96: return new StickImpl<96>(order, rad);
+    }
+    return nullptr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -245,4 +298,12 @@ void* hgr_latch_create(int dtype, int N, int width, double thresh, double ratio)
 void hgr_latch_destroy(void* h) { delete (LatchBase*)h; }
 void hgr_latch_process(void* h, const void* zre, const void* zim, void* ore, void* oim, void* level, long L) { ((LatchBase*)h)->process(zre, zim, ore, oim, level, L); }
 void hgr_latch_process_real(void* h, const void* in, void* out, long L) { ((LatchBase*)h)->process_real(in, out, L); }
+
+void* hgr_slide_create(int dtype, int N, int order, const double* rr, const double* ri) {
+    return dtype == 0 ? (void*)make_slide<float>(N, order, rr, ri) : (void*)make_slide<double>(N, order, rr, ri);
+}
+void* hgr_stick_create(int dtype, int N, int order, double rad) { return dtype == 1 ? (void*)make_stick(N, order, rad) : nullptr; }
+void hgr_casc_destroy(void* h) { delete (CascBase*)h; }
+void hgr_casc_process(void* h, const void* xre, const void* xim, void* ore, void* oim, long L) { ((CascBase*)h)->process(xre, xim, ore, oim, L); }
+void hgr_stick_rmod(void* h, double rad) { ((CascBase*)h)->rmod(rad); }
 }

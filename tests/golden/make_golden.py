@@ -66,6 +66,34 @@ def latchbank_case(dtype):
     return dict(N=N, width=width, thresh=0.35, ratio=0.2, zre=zre, zim=zim, out_re=ore, out_im=oim, level=lv)
 
 
+def cascade_input(N, L, dtype):
+    t = np.arange(L)
+    z = np.stack([(0.3 + 0.7 * design.white_noise(L, stream=40 + n)) * np.exp(1j * (0.01 * (n + 1) * t)) for n in range(N)])
+    z[:, 200:230] = 0.0                            # a stretch of exact zeros (sign-of-zero paths)
+    return z.astype(np.complex64 if dtype == np.float32 else np.complex128)
+
+
+def slidebank_case(dtype):
+    N, L, order = 8, 600, 3
+    radii = np.array([0.999 * np.exp(1j * 0.002 * n) * (1 - 0.01 * n) for n in range(N)])
+    z = cascade_input(N, L, dtype)
+    bank = oracle.RefSlidebank(N, order, radii, dtype=dtype)
+    out = np.concatenate([bank.process(z[:, :257]), bank.process(z[:, 257:])], axis=1)
+    return dict(N=N, order=order, radii=radii, z=z, split=257, out=out)
+
+
+def stickbank_case():
+    N, L = 8, 600
+    z = cascade_input(N, L, np.float64)
+    res = {}
+    for order, rad in ((1, -0.9), (1, -0.999), (2, 0.3)):
+        bank = oracle.RefStickbank(N, order, rad)
+        a = bank.process(z[:, :300])
+        bank.rmod(rad * 0.5)
+        res[f"out_{order}_{rad}"] = np.concatenate([a, bank.process(z[:, 300:])], axis=1)
+    return dict(N=N, z=z, split=300, cases=np.array([[1, -0.9], [1, -0.999], [2, 0.3]]), **res)
+
+
 def main():
     assert oracle.ref_lib() is not None, "oracle/_ref is not built"
     for dtype, tag in ((np.float32, "f32"), (np.float64, "f64")):
@@ -74,6 +102,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"oscbank_{tag}.npz"), **oscbank_case(dtype))
         np.savez_compressed(os.path.join(HERE, f"rmsbank_{tag}.npz"), **rmsbank_case(dtype))
         np.savez_compressed(os.path.join(HERE, f"latchbank_{tag}.npz"), **latchbank_case(dtype))
+        np.savez_compressed(os.path.join(HERE, f"slidebank_{tag}.npz"), **slidebank_case(dtype))
+    np.savez_compressed(os.path.join(HERE, "stickbank_f64.npz"), **stickbank_case())
     print("written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

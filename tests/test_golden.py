@@ -34,7 +34,7 @@ def _run_fb(cls, g, dtype, **kw):
 
 
 def test_golden_files_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) == 10
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) == 13
 
 
 @pytest.mark.parametrize("tag,dtype", TAGS)
@@ -105,3 +105,49 @@ def test_cuda_reproduces_golden_osc_rms(tag, dtype):
     g = np.load(os.path.join(GOLD, f"rmsbank_{tag}.npz"))
     out = hb.RMSbank(int(g["N"]), int(g["width"]), dtype=dtype).process(g["zre"], g["zim"])
     assert same(out, g["out"])
+
+
+def _run_slide(cls, g, dtype, **kw):
+    bank = cls(int(g["N"]), int(g["order"]), g["radii"], dtype=dtype, **kw)
+    sp = int(g["split"])
+    return np.concatenate([bank.process(g["z"][:, :sp]), bank.process(g["z"][:, sp:])], axis=1)
+
+
+def _run_stick(cls, g, order, rad, **kw):
+    bank = cls(int(g["N"]), order, rad, dtype=np.float64, **kw)
+    sp = int(g["split"])
+    a = bank.process(g["z"][:, :sp])
+    bank.rmod(rad * 0.5)
+    return np.concatenate([a, bank.process(g["z"][:, sp:])], axis=1)
+
+
+def _same_c(a, b):
+    return same(np.ascontiguousarray(a.real), np.ascontiguousarray(b.real)) and same(np.ascontiguousarray(a.imag), np.ascontiguousarray(b.imag))
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_oracle_reproduces_golden_slidebank(oracle_lib, tag, dtype):
+    g = np.load(os.path.join(GOLD, f"slidebank_{tag}.npz"))
+    assert _same_c(_run_slide(oracle.Slidebank, g, dtype), g["out"])
+
+
+def test_oracle_reproduces_golden_stickbank(oracle_lib):
+    g = np.load(os.path.join(GOLD, "stickbank_f64.npz"))
+    for order, rad in g["cases"]:
+        assert _same_c(_run_stick(oracle.Stickbank, g, int(order), float(rad)), g[f"out_{int(order)}_{float(rad)}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_cuda_reproduces_golden_slidebank(tag, dtype):
+    import huygens_b200 as hb
+    g = np.load(os.path.join(GOLD, f"slidebank_{tag}.npz"))
+    assert _same_c(_run_slide(hb.Slidebank, g, dtype), g["out"])
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_stickbank():
+    import huygens_b200 as hb
+    g = np.load(os.path.join(GOLD, "stickbank_f64.npz"))
+    for order, rad in g["cases"]:
+        assert _same_c(_run_stick(hb.Stickbank, g, int(order), float(rad)), g[f"out_{int(order)}_{float(rad)}"])

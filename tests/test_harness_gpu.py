@@ -65,7 +65,7 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
     r = subprocess.run([os.path.join(harness, "banks_demo"), str(ticks)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
-    assert got.shape == (ticks, 7)
+    assert got.shape == (ticks, 9)
     osc = oracle.Oscbank(8)
     for i in range(8):
         osc.freqmod(i, 110.0 * (i + 1))
@@ -79,6 +79,9 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
     assert np.array_equal(got[:, 2], first[0]) and np.array_equal(got[:, 3], again[0])
     gated = oracle.Latchbank(8, 0.9, 0.2, width=16).process(zre, zim)[0]
     assert np.allclose(got[:, 6], gated.sum(axis=0), rtol=0, atol=1e-13)
+    radii = np.array([complex(0.99 - 0.01 * i, 0.002 * i) for i in range(8)])
+    smoothed = oracle.Stickbank(8, 1, -0.9).process(oracle.Slidebank(8, 2, radii).process(ph.T))
+    assert np.allclose(got[:, 7] + 1j * got[:, 8], smoothed.sum(axis=0), rtol=0, atol=1e-13)
     F = oracle.Filterbank(2, 4, 0.001, 1.0, fixed=True)
     for i in range(4):
         F.coefficients(i, [0.5, 0, -0.5], [-1.6 + 0.1 * i, 0.81])

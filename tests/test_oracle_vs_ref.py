@@ -132,3 +132,47 @@ def test_latchbank_restatement_equals_reference(oracle_lib, N, width, dtype):
     assert 0.05 < np.mean(r[0] != 0) < 0.95                 # the gate both opens and closes
     lv = np.abs(zre) + 0.01
     assert same(oracle.Latchbank(N, 0.35, 0.3, dtype=dtype).process_real(lv), oracle.RefLatchbank(N, 0.35, 0.3, dtype=dtype).process_real(lv))
+
+
+def _casc_input(N, L, dtype, seed=3):
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((N, L)) + 1j * rng.standard_normal((N, L))
+    z[:, L // 3:L // 3 + 17] = 0.0                            # exact zeros: the alpha*rhs products' zero signs
+    z[:, L // 2] = -0.0
+    return z.astype(np.complex64 if dtype == np.float32 else np.complex128)
+
+
+def _same_c(a, b):
+    return same(np.ascontiguousarray(a.real), np.ascontiguousarray(b.real)) and same(np.ascontiguousarray(a.imag), np.ascontiguousarray(b.imag))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("order", [0, 1, 2, 5])
+@pytest.mark.parametrize("N", oracle.REF_CASC_N)
+def test_slidebank_restatement_equals_reference(oracle_lib, N, order, dtype):
+    """Slidebank's sparse-matrix cascade (src/slidebank.h:61-97,166-175), complex and real input, block splits."""
+    L = 700
+    rng = np.random.default_rng(N + order)
+    radii = rng.uniform(0.5, 0.9995, N) * np.exp(1j * rng.uniform(-0.2, 0.2, N))
+    z = _casc_input(N, L, dtype)
+    r = oracle.RefSlidebank(N, order, radii, dtype=dtype)
+    m = oracle.Slidebank(N, order, radii, dtype=dtype)
+    for a, b in ((0, 1), (1, 300), (300, L)):
+        assert _same_c(m.process(z[:, a:b]), r.process(z[:, a:b]))
+    assert _same_c(m.process(z.real[:, :50]), r.process(z.real[:, :50]))      # the ArrayT overload (:109-115)
+
+
+@pytest.mark.parametrize("order,rad", [(1, -0.9), (1, -0.999), (0, -0.5), (2, 0.3), (3, 0.2)])
+@pytest.mark.parametrize("N", oracle.REF_CASC_N)
+def test_stickbank_restatement_equals_reference(oracle_lib, N, order, rad):
+    """Stickbank's all-pole smoother (src/stickbank.h:46-79,181-218) incl. rmod and coefficients(); the
+    reference template only compiles for double."""
+    L = 600
+    z = _casc_input(N, L, np.float64, seed=11)
+    r = oracle.RefStickbank(N, order, rad)
+    m = oracle.Stickbank(N, order, rad)
+    assert _same_c(m.process(z[:, :250]), r.process(z[:, :250]))
+    r.rmod(rad * 0.7)
+    m.rmod(rad * 0.7)
+    assert _same_c(m.process(z[:, 250:]), r.process(z[:, 250:]))
+    assert np.isfinite(r.process(z[:, :10])).all()
