@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=None, help="override block length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan", action="store_true", help="skip the scan-mode side measurement")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's filters are split over the GPUs (BASELINE configs[2]) instead of N filters per GPU")
     ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
 
@@ -64,7 +65,9 @@ def parse():
 def bank_params(w, rank, world):
     from huygens_b200 import design
     from huygens_b200.sharding import filter_range
-    lo, hi = filter_range(w["N"] * world, rank, world)     # weak scaling: N filters per GPU
+    if w.get("streams", 1) > 1:                            # stream-partitioned: the same bank on every GPU, no exchange
+        rank, world = 0, 1
+    lo, hi = filter_range(w["N"] * world, rank, world)     # rank's slice of an N*world bank (N filters per GPU)
     freqs = design.log_spaced(w["N"] * world, w["f_lo"], w["f_hi"])[lo:hi]
     return design.resonator_bank(freqs, w["r"])
 
@@ -198,8 +201,9 @@ def workload_config(w, args, world):
     sname = f"{w['streams']} streams x " if w.get("streams", 1) > 1 else ""
     return {"workload": f"Filterbank<{tname}> {sname}{w['N']} log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, "
                         f"fwd {{1,0,-1}}, k_p={w['k_p']}, k_g={w['k_g']}), {w['seconds']} s 48 kHz {w['input']}, summed output",
-            "filters_per_gpu": w["N"], "filters_total": w["N"] * world, "samples": int(w["seconds"] * SR),
-            "partition": "filters" if world > 1 else "none", "mode": args.mode, "arith": args.arith,
+            "filters_per_gpu": w["N"], "filters_total": w["N"] * (1 if w.get("streams", 1) > 1 else world),
+            "streams_total": w.get("streams", 1) * (world if w.get("streams", 1) > 1 else 1), "samples": int(w["seconds"] * SR),
+            "partition": ("streams" if w.get("streams", 1) > 1 else "filters") if world > 1 else "none", "mode": args.mode, "arith": args.arith,
             "l2": "flushed between steps (256 MiB write)"}
 
 
@@ -211,6 +215,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.strong and world > 1 and w.get("streams", 1) == 1:
+        if w["N"] % world:
+            raise SystemExit(f"--strong: {w['N']} filters do not split over {world} GPUs")
+        w["N"] //= world
     if args.impl == "reference":
         run_reference(args, w, rank, world)
         return
@@ -243,9 +251,11 @@ def main():
         else:
             fb.process(xi, out=oi, mode=args.mode)
 
+    exchange = world > 1 and S == 1            # filter-partitioned: one reduce of the partial sums; stream-partitioned: none
+
     def step():
         render(x, out)
-        if world > 1:
+        if exchange:
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
 
     for _ in range(max(args.warmup, 3)):
@@ -268,7 +278,7 @@ def main():
         kev[i][0].record()
         render(x, out)
         kev[i][1].record()
-        if world > 1:
+        if exchange:
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
         ev[i][1].record()
     torch.cuda.synchronize()
@@ -300,7 +310,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         render_host()                                # synchronises before returning
-        if world > 1:
+        if exchange:
             # partial sums meet on rank 0: host -> device -> reduce would double count copies; the
             # device-side reduce of the staged output is what a sharded caller does
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
@@ -353,7 +363,8 @@ def main():
     line = {
         "metric": "filter-samples/s (biquad bank)", "value": value, "unit": "filter-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.get("dtype", "f32"), "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1 and S == 1) else "weak", "vs_baseline": None,
+        "dtype": w.get("dtype", "f32"), "data": "synthetic",
         "config": workload_config(w, args, world),
         "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * x_host.element_size()), "d2h_bytes_per_step": int(S * L * x_host.element_size() + (env_h.nbytes if args.env else 0))},
         "gpu_launches": launches_per_step * args.steps,
