@@ -369,7 +369,11 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.c_p = (T)fb->c_p; P.s_p = (T)fb->s_p; P.c_g = (T)fb->c_g; P.s_g = (T)fb->s_g;
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
-        if (F == 0) rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
+        P.sm_slot = fb->d_sm_slot;
+        if (F == 0) {
+            if (fb->ws_level > 0) HG_CUDA(cudaMemsetAsync(fb->d_sm_slot, 0, 1024 * sizeof(int), st));
+            rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
+        }
         else if (F == -2) {
             FbEnvArgs<T> E;
             if (fb->cur_env) {

@@ -78,7 +78,8 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     if ((ce = cudaMallocHost(&fb->h_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_state, 4 * S * N * es)) != cudaSuccess ||
-        (ce = cudaMalloc(&fb->d_xh, 2 * S * 2 * es)) != cudaSuccess ) {
+        (ce = cudaMalloc(&fb->d_xh, 2 * S * 2 * es)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&fb->d_sm_slot, 1024 * sizeof(int))) != cudaSuccess ) {
         hg_fb_destroy(fb);
         return hg::fail(HG_ERR_NOMEM, "hg_fb_create: allocation failed: %s", cudaGetErrorString(ce));
     }
@@ -98,6 +99,7 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_par) cudaFree(fb->d_par);
     if (fb->d_state) cudaFree(fb->d_state);
     if (fb->d_xh) cudaFree(fb->d_xh);
+    if (fb->d_sm_slot) cudaFree(fb->d_sm_slot);
     fb->in_stage.release(); fb->out_stage.release(); fb->bands_stage.release(); fb->partial.release();
     fb->scan_a.release(); fb->scan_b.release(); fb->env_stage.release();
     if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);

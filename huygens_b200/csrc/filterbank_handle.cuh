@@ -37,6 +37,7 @@ struct hg_fb {
     void* cur_env_out = nullptr; // device pointer of the block's envelope output, may be null
     int cur_hop = 0;
     size_t cur_env_rows = 0;
+    int* d_sm_slot = nullptr;        // per-SM CTA arrival counters (role rotation of co-resident ws CTAs)
     hg::DevBuf env_stage;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
 };
 
@@ -58,6 +59,7 @@ template <typename T> struct FbK1Params {
     int bands_vec;
     int dist;      // HG_DIST_*: per-band nonlinearity before the sum (lane kernel only)
     int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
+    int* sm_slot;  // [>= SM count] zeroed before a launch with several CTAs per SM: arrival order of the CTAs on each SM
 };
 
 template <typename T>
