@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan", action="store_true", help="skip the scan-mode side measurement")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's filters are split over the GPUs (BASELINE configs[2]) instead of N filters per GPU")
+    ap.add_argument("--followers", default="replica", choices=["ring", "replica"], help="with --env: how y[t-width] is obtained (HBM ring, or lagged replica filters)")
     ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
 
@@ -247,7 +248,7 @@ def main():
 
     def render(xi, oi):
         if args.env:
-            fb.process_env(xi, width=2400, hop=64, out=oi, env=env_buf)
+            fb.process_env(xi, width=2400, hop=64, out=oi, env=env_buf, followers=args.followers)
         else:
             fb.process(xi, out=oi, mode=args.mode)
 
@@ -298,7 +299,7 @@ def main():
 
     def render_host():
         if args.env:
-            fb.process_env(xh, width=2400, hop=64, out=oh, env=env_h)   # envelopes come back to the host too
+            fb.process_env(xh, width=2400, hop=64, out=oh, env=env_h, followers=args.followers)   # envelopes come back to the host too
         else:
             fb.process(xh, out=oh, mode=args.mode)
 
@@ -379,7 +380,7 @@ def main():
                      "bit_exact_floor_ms": L * chain_cycles / (peak["sm_mhz"] * 1e3) if peak["sm_mhz"] else None, "mode": info["mode"], "filters_per_thread": info["filters_per_thread"],
                      "ctas": info["ctas"]},
     }
-    if args.env:
+    if args.env and args.followers == "ring":
         # the fused envelope followers add 8 B of ring traffic per filter-sample (read q[t-width], write q[t]):
         # that kernel is HBM-bound, so its roofline is the measured copy bandwidth
         try:
@@ -392,6 +393,13 @@ def main():
                             "peak_source": src, "bytes_per_unit": 8, "kernel_ms": t_kernel / args.steps * 1e3,
                             "fma_frac": achieved / peak["slots_per_s"], "mode": info["mode"], "ctas": info["ctas"],
                             "note": "Filterbank + per-band RMSbank(2400) followers, ring of y^2 in HBM; envelopes every 64 samples"}
+    elif args.env:
+        # replica followers: no ring; algorithmic work per filter-sample = the filter (11 slots) + the follower
+        # (y*y, q - q_old, + S: 3 slots).  The lagged replica that regenerates q_old is overhead, not counted.
+        slots = SLOTS_PER_FILTER_SAMPLE + 3
+        line["roofline"].update({"achieved": per_gpu_kernel * slots / 1e12, "frac": per_gpu_kernel * slots / peak["slots_per_s"],
+                                 "frac_of_nominal": per_gpu_kernel * slots / nominal, "slots_per_unit": slots,
+                                 "note": "Filterbank + per-band RMSbank(2400) followers; y[t-2400] regenerated by lagged replica filters (no ring); envelopes every 64 samples"})
     if scan_info:
         line["scan"] = scan_info
     if not args.no_cpu_baseline:

@@ -345,6 +345,16 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         HG_TRY(fb->partial.reserve((size_t)rows * fb->S * seg * sizeof(T)));
     }
     const bool vec_ok = d_bands && (((uintptr_t)d_bands) % 16 == 0) && (L % 4 == 0);
+    // replica followers: history + block in one row per stream, so that the lagged input x[t - width] of
+    // block tick t is xcat[4 + t] (four leading samples keep x[t-1], x[t-2] of the lagged stream addressable
+    // and the rows 16-byte aligned)
+    const bool replica = F == -2 && fb->cur_env && fb->env_mode == 2;
+    const size_t H = (size_t)fb->rms_width + 4, pitch = H + L;
+    if (replica) {
+        HG_TRY(fb->xcat.reserve((size_t)fb->S * pitch * sizeof(T)));
+        HG_CUDA(cudaMemcpy2DAsync(fb->xcat.p, pitch * sizeof(T), fb->d_xhist, H * sizeof(T), H * sizeof(T), fb->S, cudaMemcpyDeviceToDevice, st));
+        HG_CUDA(cudaMemcpy2DAsync((T*)fb->xcat.p + H, pitch * sizeof(T), d_in, L * sizeof(T), L * sizeof(T), fb->S, cudaMemcpyDeviceToDevice, st));
+    }
     for (size_t t0 = 0; t0 < L; t0 += seg) {
         const size_t len = (L - t0 < seg) ? (L - t0) : seg;
         FbK1Params<T> P;
@@ -380,6 +390,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
                 E.env = (T*)fb->cur_env_out; E.rms_sum = (T*)fb->d_rms_sum; E.rms_ring = (T*)fb->d_rms_ring;
                 E.width = fb->rms_width; E.hop = fb->cur_hop; E.env_rows = (long)fb->cur_env_rows;
                 E.t_base = (long)t0; E.tick0 = fb->rms_ticks;
+                if (replica) { E.in_lag = (const T*)fb->xcat.p + 4 + t0; E.lag_stride = (long)pitch; E.lag_state = (T*)fb->d_lag_state; }
             }
             rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st, fb->cur_env ? &E : nullptr);
         }
@@ -394,6 +405,8 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
             fb->last_launches++;
         }
     }
+    if (replica)       // the last width + 4 samples become the history of the next block
+        HG_CUDA(cudaMemcpy2DAsync(fb->d_xhist, H * sizeof(T), (const T*)fb->xcat.p + L, pitch * sizeof(T), H * sizeof(T), fb->S, cudaMemcpyDeviceToDevice, st));
     return HG_OK;
 }
 

@@ -104,6 +104,9 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     fb->scan_a.release(); fb->scan_b.release(); fb->env_stage.release();
     if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);
     if (fb->d_rms_ring) cudaFree(fb->d_rms_ring);
+    if (fb->d_lag_state) cudaFree(fb->d_lag_state);
+    if (fb->d_xhist) cudaFree(fb->d_xhist);
+    fb->xcat.release();
     delete fb;
     return HG_OK;
 }
@@ -246,14 +249,31 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
     HG_CUDA(cudaSetDevice(fb->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t es = hg::dtype_size(fb->dtype), S = fb->S, N = fb->N;
+    if (fb->env_mode == 2 && fb->dirty && fb->d_rms_sum)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process_env: replica followers replay the filters %d ticks late and cannot follow a parameter change; use HG_ENV_RING", width);
     if (!fb->d_rms_sum) {
-        // RMSbank(width) per (stream, filter): running sums and the ring of the last `width` squares, zeroed (rmsbank.h:34-44)
+        // RMSbank(width) per (stream, filter): running sums zeroed (rmsbank.h:34-44) and either the ring of the
+        // last `width` squares (zeroed) or the lagged replicas (state of the filters now, idle for `width` ticks)
         cudaError_t ce;
-        if ((ce = cudaMalloc(&fb->d_rms_sum, S * N * es)) != cudaSuccess ||
-            (ce = cudaMalloc(&fb->d_rms_ring, S * (size_t)width * ((N + 31) / 32 * 32) * es)) != cudaSuccess)
-            return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower state (%zu bytes): %s", S * (size_t)width * N * es, cudaGetErrorString(ce));
+        if ((ce = cudaMalloc(&fb->d_rms_sum, S * N * es)) != cudaSuccess)
+            return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower sums: %s", cudaGetErrorString(ce));
         HG_CUDA(cudaMemsetAsync(fb->d_rms_sum, 0, S * N * es, st));
-        HG_CUDA(cudaMemsetAsync(fb->d_rms_ring, 0, S * (size_t)width * ((N + 31) / 32 * 32) * es, st));
+        if (fb->env_mode == 2) {
+            const size_t H = (size_t)width + 4;
+            if ((ce = cudaMalloc(&fb->d_lag_state, 3 * S * N * es)) != cudaSuccess ||
+                (ce = cudaMalloc(&fb->d_xhist, S * H * es)) != cudaSuccess)
+                return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: replica state: %s", cudaGetErrorString(ce));
+            HG_CUDA(cudaMemcpyAsync(fb->d_lag_state, fb->d_state, 3 * S * N * es, cudaMemcpyDeviceToDevice, st));
+            HG_CUDA(cudaMemsetAsync(fb->d_xhist, 0, S * H * es, st));
+            // the two input samples before the followers start: x[t-1], x[t-2] of every stream
+            const char* xh = (const char*)fb->d_xh + (size_t)fb->xh_cur * 2 * S * es;
+            HG_CUDA(cudaMemcpy2DAsync((char*)fb->d_xhist + (H - 1) * es, H * es, xh, 2 * es, es, S, cudaMemcpyDeviceToDevice, st));
+            HG_CUDA(cudaMemcpy2DAsync((char*)fb->d_xhist + (H - 2) * es, H * es, xh + es, 2 * es, es, S, cudaMemcpyDeviceToDevice, st));
+        } else {
+            if ((ce = cudaMalloc(&fb->d_rms_ring, S * (size_t)width * ((N + 31) / 32 * 32) * es)) != cudaSuccess)
+                return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower ring (%zu bytes): %s", S * (size_t)width * N * es, cudaGetErrorString(ce));
+            HG_CUDA(cudaMemsetAsync(fb->d_rms_ring, 0, S * (size_t)width * ((N + 31) / 32 * 32) * es, st));
+        }
         fb->rms_width = width;
         fb->rms_ticks = 0;
     }
@@ -274,6 +294,14 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
         HG_CUDA(cudaMemcpyAsync(out_env, d_env, S * rows * N * es, cudaMemcpyDeviceToHost, st));
         HG_CUDA(cudaStreamSynchronize(st));
     }
+    return HG_OK;
+}
+
+hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: null handle");
+    if (mode != HG_ENV_RING && mode != HG_ENV_REPLICA) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: bad mode %d", mode);
+    if (fb->d_rms_sum && mode != fb->env_mode) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: the followers are already running");
+    fb->env_mode = mode;
     return HG_OK;
 }
 

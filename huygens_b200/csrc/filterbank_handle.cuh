@@ -37,6 +37,10 @@ struct hg_fb {
     void* cur_env_out = nullptr; // device pointer of the block's envelope output, may be null
     int cur_hop = 0;
     size_t cur_env_rows = 0;
+    int env_mode = 1;            // HG_ENV_RING (1) or HG_ENV_REPLICA (2), fixed once the followers have started
+    void* d_lag_state = nullptr; // replica followers: [3][S][N] y1, y2, p of the lagged copies
+    void* d_xhist = nullptr;     // replica followers: [S][width + 4] input samples before the current block
+    hg::DevBuf xcat;             // replica followers: [S][width + 4 + L] history + block
     int* d_sm_slot = nullptr;        // per-SM CTA arrival counters (role rotation of co-resident ws CTAs)
     hg::DevBuf env_stage;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
 };
@@ -73,6 +77,9 @@ template <typename T> struct FbEnvArgs {
     int width, hop;
     long env_rows, t_base;
     long long tick0;
+    const T* in_lag = nullptr;    // replica followers: lagged input of this launch (null => ring followers)
+    long lag_stride = 0;
+    T* lag_state = nullptr;
 };
 template <typename T>
 hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st,

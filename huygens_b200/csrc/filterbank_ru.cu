@@ -81,14 +81,16 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
 //   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[2][NS][32] | barriers
 template <typename T> struct Layout {
     static constexpr int RS = RowStride<T>::RS;
-    int W, NS;
-    __host__ __device__ explicit Layout(int w) : W(w), NS(s_warps(w)) {}
+    int W, NS, LAG;       // LAG: the replica followers add a second input ring
+    __host__ __device__ explicit Layout(int w, bool lag = false) : W(w), NS(s_warps(w)), LAG(lag ? 1 : 0) {}
     __host__ __device__ size_t xs_off() const { return 0; }
     __host__ __device__ size_t y_off() const { return sizeof(T) * XB * XT; }
     __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NB * 32 * RS; }
     __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * NS * 32 * RS; }
     __host__ __device__ size_t ps_off() const { return gs_off() + sizeof(T) * NS * GPS * 32; }
-    __host__ __device__ size_t bar_off() const { return (ps_off() + sizeof(T) * 2 * NS * 32 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xl_off() const { return (ps_off() + sizeof(T) * 2 * NS * 32 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t yl_off() const { return xl_off() + sizeof(T) * (size_t)LAG * XB * XT; }
+    __host__ __device__ size_t bar_off() const { return (yl_off() + 15) & ~(size_t)15; }
     __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB + 4); }
 };
 
@@ -141,6 +143,36 @@ __device__ __forceinline__ void ru_tile(const T* __restrict__ xc, T* __restrict_
     }
 }
 
+// ENV == 2: a full tile of the filter AND of its `width`-lagged replica, interleaved (two independent
+// dependency chains per lane), with the envelope follower folded in: q = y^2, q_old = (replica y)^2,
+// S <- (q - q_old) + S  (rmsbank.h:58-61; the "+ 0*0" of a real sample's |z|^2 is exact for q >= 0 and dropped).
+// S after tick `je` of the tile (if 0 <= je < TILE) is returned in s_at_je for the envelope row.
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* __restrict__ xlc, T* __restrict__ yrow,
+                                            T b0, T b1, T b2, T a1, T a2, T p, T pl,
+                                            T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2,
+                                            T& y1l, T& y2l, T& x1l, T& x2l, T& m1l, T& m2l, T& t2l,
+                                            T& rsum, int je, T& s_at_je) {
+    using namespace ru;
+    typedef Ar<T, FMA> A;
+    T xq[2][4], xlq[2][4];
+    ld4<T>(xc, xq[0]);
+    ld4<T>(xlc, xlq[0]);
+#pragma unroll
+    for (int q = 0; q < TILE / 4; q++) {
+        if (q + 1 < TILE / 4) { ld4<T>(xc + 4 * (q + 1), xq[(q + 1) & 1]); ld4<T>(xlc + 4 * (q + 1), xlq[(q + 1) & 1]); }
+        T yy[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            yy[j] = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+            const T yl = ru_sample<T, FMA, TAPS>(xlq[q & 1][j], b0, b1, b2, a1, a2, pl, y1l, y2l, x1l, x2l, m1l, m2l, t2l);
+            rsum = A::add(A::sub(A::mul(yy[j], yy[j]), A::mul(yl, yl)), rsum);
+            if (4 * q + j == je) s_at_je = rsum;
+        }
+        st4<T>(yrow + 4 * q, yy);
+    }
+}
+
 template <typename T> struct FbRuParams {
     FbK1Params<T> k;
     int W;            // RU warps per CTA
@@ -154,10 +186,16 @@ template <typename T> struct FbRuParams {
     long env_rows;
     long t_base;          // first sample of this launch within the block
     long long tick0;      // ticks rendered before this block (ring position)
+    // ENV == 2, replica followers: y[t-width] is regenerated by a second copy of every filter that runs
+    // `width` ticks behind (same arithmetic, same input => same bits), instead of being stored
+    const T* in_lag;      // per stream: in_lag[t] = x[t - width] for launch-relative t (t = -1, -2 valid)
+    long lag_stride;
+    T* lag_state;         // [3][S][N]: y1, y2, p of the replicas
 };
 
-template <typename T, bool FMA, bool BANDS, bool ENV>
-__global__ void __launch_bounds__(ENV ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV)) * 32 : (ru::W_MAX + ru::NS_MAX) * 32, 1)
+// ENV: 0 no followers; 1 followers with the ring of y^2 in HBM; 2 followers with lagged replicas
+template <typename T, bool FMA, bool BANDS, int ENV>
+__global__ void __launch_bounds__(ENV == 1 ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV)) * 32 : (ru::W_MAX + ru::NS_MAX) * 32, 1)
 fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
@@ -166,8 +204,9 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     const int W = Q.W;
     const int NS = s_warps(W);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Layout<T> lay(W);
+    const Layout<T> lay(W, ENV == 2);
     T* xs = reinterpret_cast<T*>(smem_raw + lay.xs_off());
+    T* xls = reinterpret_cast<T*>(smem_raw + lay.xl_off());          // ENV == 2: lagged input ring
     T* ytiles = reinterpret_cast<T*>(smem_raw + lay.y_off());
     T* gtiles = reinterpret_cast<T*>(smem_raw + lay.gt_off());
     T* gsmem = reinterpret_cast<T*>(smem_raw + lay.gs_off());
@@ -229,18 +268,32 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         const T wT = (T)Q.width;
         // ring layout [S][filter group of 32][width][32]: a warp's consecutive positions are consecutive 128-byte
         // lines, so a tile of 32 samples is one contiguous 4 KB burst (DRAM-row friendly)
-        T* ring = ENV ? Q.rms_ring + (((size_t)s * groups + (w_first + warp)) * Q.width) * 32 + lane : nullptr;
-        int rpos = ENV ? (int)((Q.tick0 + Q.t_base) % Q.width) : 0;
+        T* ring = ENV == 1 ? Q.rms_ring + (((size_t)s * groups + (w_first + warp)) * Q.width) * 32 + lane : nullptr;
+        int rpos = ENV == 1 ? (int)((Q.tick0 + Q.t_base) % Q.width) : 0;
+        // ENV == 2: the replica of this lane, idle until the stream is `width` ticks old
+        T y1l = (T)0, y2l = (T)0, pl = (T)0, x1l = (T)0, x2l = (T)0, m1l = (T)0, m2l = (T)0, t2l = (T)0;
+        bool convl = false, was_idle = false;
+        long lag_left = 0;
+        const T* inl = nullptr;
+        if (ENV == 2) {
+            if (ok) { y1l = Q.lag_state[0 * SN + si]; y2l = Q.lag_state[1 * SN + si]; pl = Q.lag_state[2 * SN + si]; }
+            inl = Q.in_lag + (size_t)s * Q.lag_stride;
+            const long long started = Q.tick0 + Q.t_base - Q.width;      // replica ticks already done (< 0: idle)
+            lag_left = started < 0 ? (long)(-started) : 0;
+            x1l = inl[-1]; x2l = inl[-2];
+            m1l = A::mul(b0, x1l); m2l = A::mul(b0, x2l); t2l = A::mul(a2, y2l);
+            convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+        }
         long hop_left = ENV ? (long)Q.hop - (Q.t_base % Q.hop) : 0;        // samples until the next envelope row
         long env_row = ENV ? Q.t_base / Q.hop : 0;
         // ENV: the delayed squares q[t-width] live in one register buffer that is refilled in place: as soon as
         // slot j of tile k has been consumed, slot j of tile k+1 is requested, so every ring load has a whole
         // tile of arithmetic to land (width >= 2 * TILE keeps the two tiles' positions apart)
-        T qo[ENV ? TILE : 1];
-        if (ENV && ok) {
+        T qo[ENV == 1 ? TILE : 1];
+        if (ENV == 1 && ok) {
             const int cnt0 = (ntiles == 1) ? last_tn : TILE;
 #pragma unroll
-            for (int j = 0; j < (ENV ? TILE : 1); j++) {
+            for (int j = 0; j < (ENV == 1 ? TILE : 1); j++) {
                 int pj = rpos + j;
                 if (pj >= Q.width) pj -= Q.width;
                 qo[j] = (j < cnt0) ? ring[(size_t)pj * 32] : (T)0;
@@ -253,7 +306,24 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             const T* xc = xs + xb * XT + kc * TILE;
             T* yrow = ybase + yb * 32 * RS;
             int tt = 0;
-            if (conv && tn == TILE) {
+            bool fused = false;
+            if (ENV == 2 && conv && convl && lag_left == 0 && !was_idle && tn == TILE && Q.hop >= TILE) {
+                // filter + replica + follower in one unrolled tile
+                const T* xlc = xls + xb * XT + kc * TILE;
+                const int je = hop_left <= TILE ? (int)hop_left - 1 : -1;
+                T s_je = (T)0;
+                if (taps == 2) ru_tile_env<T, FMA, 2>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                else if (taps == 1) ru_tile_env<T, FMA, 1>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                else ru_tile_env<T, FMA, 0>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                if (je >= 0) {
+                    if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(s_je, wT));   // rmsbank.h:64
+                    env_row++;
+                    hop_left += Q.hop;
+                }
+                hop_left -= TILE;
+                tt = TILE;
+                fused = true;
+            } else if (conv && tn == TILE) {
                 // whole tile unrolled; `taps` is uniform, so pick the specialised body once per tile
                 if (taps == 2) ru_tile<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                 else if (taps == 1) ru_tile<T, FMA, 1>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
@@ -283,7 +353,44 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             }
             if (!conv || tn != TILE) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
             if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
-            if (ENV && ok) {
+            if (ENV == 2 && !fused) {
+                // replica + follower, sample by sample (stream start, smoothers still moving, ragged tile, hop < TILE)
+                const T* xlc = xls + xb * XT + kc * TILE;
+                int j0 = 0;                                                       // ticks of this tile before the replica starts
+                if (lag_left > 0) { j0 = (int)min((long)tn, lag_left); lag_left -= j0; was_idle = true; }
+                if (was_idle && j0 < tn) {
+                    // the replica starts in this tile: its input history is what precedes its first sample
+                    const long t1 = (long)k * TILE + j0;                          // launch-relative tick of that sample
+                    x1l = inl[t1 - 1]; x2l = inl[t1 - 2];
+                    convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+                    was_idle = false;
+                }
+                for (int j = 0; j < tn; j++) {
+                    T yl = (T)0;                                                  // idle: y[t - width] = 0 (rmsbank.h:36-44 setZero)
+                    if (j >= j0) {
+                        if (!convl) pl = A::muladd(s_p, pl, cp);
+                        const T x0 = xlc[j];
+                        T fw = A::mul(b0, x0);
+                        fw = A::muladd(b1, x1l, fw);
+                        fw = A::muladd(b2, x2l, fw);
+                        T fbk = A::mul(a1, y1l);
+                        fbk = A::muladd(a2, y2l, fbk);
+                        yl = A::mulsub(fw, pl, fbk);
+                        y2l = y1l; y1l = yl;
+                        x2l = x1l; x1l = x0;
+                    }
+                    const T y = yrow[j];
+                    rsum = A::add(A::sub(A::mul(y, y), A::mul(yl, yl)), rsum);     // rmsbank.h:58-61
+                    if (--hop_left == 0) {
+                        if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(rsum, wT));   // :64
+                        env_row++;
+                        hop_left = Q.hop;
+                    }
+                }
+                m1l = A::mul(b0, x1l); m2l = A::mul(b0, x2l); t2l = A::mul(a2, y2l);
+                if (!convl && lag_left == 0 && !was_idle) convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+            }
+            if (ENV == 1 && ok) {
                 // envelope follower over the tile just rendered (own row of the y tile), rmsbank.h:58-64
                 const int tn_next = (k + 1 >= ntiles) ? 0 : ((k + 1 == ntiles - 1) ? last_tn : TILE);
                 if (tn == TILE && tn_next == TILE && rpos + 2 * TILE <= Q.width && Q.hop >= TILE) {
@@ -345,6 +452,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         if (ok) {
             P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[2 * SN + si] = p;
             if (ENV) Q.rms_sum[si] = rsum;
+            if (ENV == 2) { Q.lag_state[0 * SN + si] = y1l; Q.lag_state[1 * SN + si] = y2l; Q.lag_state[2 * SN + si] = pl; }
         }
         if (cta == 0 && warp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
     } else {
@@ -373,6 +481,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         gconv = __all_sync(0xffffffffu, gconv);
         __syncwarp();
         const T* inp = P.in + (size_t)s * P.in_stride;
+        const T* inlp = ENV == 2 ? Q.in_lag + (size_t)s * Q.lag_stride : nullptr;
         T* out_row = P.out ? P.out + ((size_t)cta * P.S + s) * (size_t)L : nullptr;     // one partial row per CTA
         int xb = 0, yb = 0, kc = 0;
         unsigned xpar = 0, ypar = 0;
@@ -386,11 +495,19 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                     const long base = (long)c * XT;
                     const int cnt = (int)min((long)XT, L - base);
                     const T* src = inp + base;
+                    const T* srcl = ENV == 2 ? inlp + base : src;
                     const unsigned bytes = (unsigned)(cnt * sizeof(T));
-                    if ((((uintptr_t)src) & 15) == 0 && (bytes & 15) == 0) {
-                        if (lane == 0) { mbar_arrive_tx(&x_full[b], bytes); bulk_g2s(xs + b * XT, src, bytes, &x_full[b]); }
+                    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)srcl) & 15) == 0 && (bytes & 15) == 0) {
+                        if (lane == 0) {
+                            mbar_arrive_tx(&x_full[b], ENV == 2 ? 2 * bytes : bytes);
+                            bulk_g2s(xs + b * XT, src, bytes, &x_full[b]);
+                            if (ENV == 2) bulk_g2s(xls + b * XT, srcl, bytes, &x_full[b]);
+                        }
                     } else {
-                        for (int i = lane; i < cnt; i += 32) xs[b * XT + i] = src[i];
+                        for (int i = lane; i < cnt; i += 32) {
+                            xs[b * XT + i] = src[i];
+                            if (ENV == 2) xls[b * XT + i] = srcl[i];
+                        }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&x_full[b]);
                     }
@@ -488,13 +605,13 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
 template <typename T>
 void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
     const int groups = (fb->N + 31) / 32;
-    const int w_max = fb->cur_env ? ru::W_MAX_ENV : ru::W_MAX;
+    const int w_max = (fb->cur_env && fb->env_mode != 2) ? ru::W_MAX_ENV : ru::W_MAX;
     const size_t smem_sm = (size_t)227 * 1024;
     int bestW = 4;
     double best = -1;
     for (int per_sm = 1; per_sm <= 2; per_sm++) {
         for (int W = 4; W <= w_max; W++) {
-            if ((ru::Layout<T>(W).bytes() + 1024) * per_sm > smem_sm) continue;
+            if ((ru::Layout<T>(W, fb->env_mode == 2 && fb->cur_env).bytes() + 1024) * per_sm > smem_sm) continue;
             const long slots = (long)fb->sm_count * per_sm;
             const long ctas = (long)((groups + W - 1) / W) * fb->S;
             const long waves = (ctas + slots - 1) / slots;
@@ -512,9 +629,9 @@ void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
 template void fb_ru_config<float>(const hg_fb*, int*, int*);
 template void fb_ru_config<double>(const hg_fb*, int*, int*);
 
-template <typename T, bool FMA, bool BANDS, bool ENV>
+template <typename T, bool FMA, bool BANDS, int ENV>
 static hg_status launch_ru(const FbRuParams<T>& Q, cudaStream_t st) {
-    const size_t smem = ru::Layout<T>(Q.W).bytes();
+    const size_t smem = ru::Layout<T>(Q.W, ENV == 2).bytes();
     auto kern = fb_exact_ru_kernel<T, FMA, BANDS, ENV>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W)) * 32, smem, st>>>(Q);
@@ -527,14 +644,17 @@ hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W
     FbRuParams<T> Q;
     Q.k = P; Q.W = W; Q.cps = cps;
     Q.env = nullptr; Q.rms_sum = nullptr; Q.rms_ring = nullptr; Q.width = 1; Q.hop = 1; Q.env_rows = 0; Q.t_base = 0; Q.tick0 = 0;
+    Q.in_lag = nullptr; Q.lag_stride = 0; Q.lag_state = nullptr;
     if (env) {
         Q.env = env->env; Q.rms_sum = env->rms_sum; Q.rms_ring = env->rms_ring; Q.width = env->width; Q.hop = env->hop;
         Q.env_rows = env->env_rows; Q.t_base = env->t_base; Q.tick0 = env->tick0;
+        Q.in_lag = env->in_lag; Q.lag_stride = env->lag_stride; Q.lag_state = env->lag_state;
         if (bands) return fail(HG_ERR_UNSUPPORTED, "envelope followers and per-band outputs cannot be combined");
-        return fma ? launch_ru<T, true, false, true>(Q, st) : launch_ru<T, false, false, true>(Q, st);
+        if (env->in_lag) return fma ? launch_ru<T, true, false, 2>(Q, st) : launch_ru<T, false, false, 2>(Q, st);
+        return fma ? launch_ru<T, true, false, 1>(Q, st) : launch_ru<T, false, false, 1>(Q, st);
     }
-    if (bands) return fma ? launch_ru<T, true, true, false>(Q, st) : launch_ru<T, false, true, false>(Q, st);
-    return fma ? launch_ru<T, true, false, false>(Q, st) : launch_ru<T, false, false, false>(Q, st);
+    if (bands) return fma ? launch_ru<T, true, true, 0>(Q, st) : launch_ru<T, false, true, 0>(Q, st);
+    return fma ? launch_ru<T, true, false, 0>(Q, st) : launch_ru<T, false, false, 0>(Q, st);
 }
 template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, cudaStream_t, const FbEnvArgs<float>*);
 template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, cudaStream_t, const FbEnvArgs<double>*);

@@ -91,6 +91,14 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
  * [n_streams][L/hop][n_filters] receives env at block samples hop-1, 2*hop-1, ...; the follower state
  * (running sums and the ring of the last `width` squares) persists in the handle; width >= 64 and
  * fixed at the first call.  Bit-identical to Filterbank bands -> RMSbank. */
+/* How the followers obtain y[t-width].  HG_ENV_RING (default): a ring of the last `width` squares per filter
+ * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter); follows
+ * parameter changes.  HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same
+ * input and regenerates y[t-width] bit for bit (no ring, twice the arithmetic, ~1.7x faster on B200); the
+ * coefficients, boost and mix must then stay fixed once the followers run (HG_ERR_UNSUPPORTED otherwise).
+ * Call before the first hg_fb_process_env. */
+enum { HG_ENV_RING = 1, HG_ENV_REPLICA = 2 };
+hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode);
 hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_env, size_t L, int width,
                             int hop, void* cuda_stream);
 /* state access (streaming / checkpoint tests): y1,y2,p,g are [n_streams][n_filters]; xhist is
