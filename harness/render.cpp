@@ -4,7 +4,7 @@
 // synthetic buffer instead of PortAudio.  Prints one JSON line; optionally dumps the rendered floats.
 //
 //   render [--filters N] [--seconds S] [--double] [--input white|chirp] [--bsize B] [--per-sample]
-//          [--recipe resynthesis|strings] [--out file.f32]
+//          [--recipe resynthesis|strings] [--in file.wav|file.f32] [--out file.wav|file.f32]
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -73,7 +73,7 @@ template <typename T> static void fill(Filterbank<T>& bank, const std::string& r
 int main(int argc, char** argv) {
     double seconds = 1.0;
     bool dbl = false;
-    std::string input = "white", recipe = "resynthesis", out_path;
+    std::string input = "white", recipe = "resynthesis", out_path, in_path;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -85,14 +85,17 @@ int main(int argc, char** argv) {
         else if (a == "--per-sample") per_sample = true;
         else if (a == "--recipe") recipe = next();
         else if (a == "--out") out_path = next();
+        else if (a == "--in") in_path = next();
         else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
     try {
         const double k_p = recipe == "resynthesis" ? 0.1 : 0.001, k_g = 1;
         if (dbl) { bank_d.reset(new Filterbank<double>(2, N, k_p, k_g)); fill(*bank_d, recipe); }
         else { bank_f.reset(new Filterbank<float>(2, N, k_p, k_g)); fill(*bank_f, recipe); }
-        const size_t frames = (size_t)(seconds * SR);
-        std::vector<float> in = input == "chirp" ? chirp<float>(frames) : white_noise<float>(frames);
+        std::vector<float> in;
+        if (!in_path.empty()) in = read_audio(in_path);           // .wav (PCM16 / float32, first channel) or raw float32
+        else in = input == "chirp" ? chirp<float>((size_t)(seconds * SR)) : white_noise<float>((size_t)(seconds * SR));
+        const size_t frames = in.size();
         std::vector<float> out(frames);
         OfflineAudio A(process, BSIZE);
         const double t = A.render(in.data(), out.data(), frames);
@@ -101,12 +104,12 @@ int main(int argc, char** argv) {
         std::printf("{\"filters\": %d, \"frames\": %zu, \"dtype\": \"%s\", \"bsize\": %d, \"per_sample\": %s, "
                     "\"seconds_wall\": %.6f, \"filter_samples_per_s\": %.4e, \"peak\": %.9g}\n",
                     N, frames, dbl ? "f64" : "f32", BSIZE, per_sample ? "true" : "false", t, (double)N * frames / t, peak);
-        if (!out_path.empty()) {
-            std::ofstream f(out_path, std::ios::binary);
-            f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
-        }
+        if (!out_path.empty()) write_audio(out_path, out);        // .wav => float32 RIFF/WAVE, else raw float32
     } catch (const cuda_error& e) {
         std::fprintf(stderr, "huygens_cuda error %d: %s\n", e.status, e.what());
+        return 1;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
         return 1;
     }
     return 0;

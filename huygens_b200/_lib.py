@@ -35,6 +35,7 @@ SYMBOLS = [
     ("hg_fb_process", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_fb_process_env", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_fb_set_follower_mode", _i, [_vp, _i]),
+    ("hg_fb_process_events", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     ("hg_fb_get_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_set_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_last_launch", _i, [_vp, _pi, _pi, _pi, _pi]),
@@ -61,6 +62,15 @@ SYMBOLS = [
     ("hg_casc_destroy", _i, [_vp]),
     ("hg_casc_process", _i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 ]
+
+
+class FbEvent(C.Structure):
+    """hg_fb_event of include/huygens_cuda.h."""
+    _fields_ = [("tick", C.c_size_t), ("kind", C.c_int), ("n0", C.c_int), ("count", C.c_int),
+                ("a", C.c_void_p), ("na", C.c_int), ("b", C.c_void_p), ("nb", C.c_int)]
+
+
+HG_EV_COEFFICIENTS, HG_EV_BOOST, HG_EV_MIX, HG_EV_OPEN = 0, 1, 2, 3
 
 
 class HuygensError(RuntimeError):

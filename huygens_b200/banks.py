@@ -158,6 +158,34 @@ class Filterbank(_Handle):
         L.check(L.lib().hg_fb_process_env(self._h, _ptr(x), _ptr(out), _ptr(env), Ls, width, hop, stream))
         return out, env
 
+    def process_events(self, x, events, mode="exact"):
+        """Block render with setter calls at exact ticks (hg_fb_process_events): events = [(tick, kind, ...)] with
+        ("coefficients", n, forward, back) | ("boost", n0, values) | ("mix", n0, values) | ("open",), ticks ascending.
+        Equals calling the setter between ticks `tick - 1` and `tick` of the caller loop."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        out = np.empty_like(x)
+        keep, evs = [], (L.FbEvent * len(events))()
+        for i, (tick, kind, *args) in enumerate(events):
+            ev = evs[i]
+            ev.tick = int(tick)
+            if kind == "coefficients":
+                f, b = self._arr(args[1]), self._arr(args[2])
+                if f.ndim == 1:
+                    f, b = f[None, :], b[None, :]
+                keep += [f, b]
+                ev.kind, ev.n0, ev.count = L.HG_EV_COEFFICIENTS, int(args[0]), f.shape[0]
+                ev.a, ev.na, ev.b, ev.nb = f.ctypes.data, f.shape[1], b.ctypes.data, b.shape[1]
+            elif kind in ("boost", "mix"):
+                v = np.atleast_1d(self._arr(args[1]))
+                keep.append(v)
+                ev.kind, ev.n0, ev.count, ev.a = (L.HG_EV_BOOST if kind == "boost" else L.HG_EV_MIX), int(args[0]), len(v), v.ctypes.data
+            elif kind == "open":
+                ev.kind = L.HG_EV_OPEN
+            else:
+                raise ValueError(f"unknown event kind {kind!r}")
+        L.check(L.lib().hg_fb_process_events(self._h, _ptr(x), _ptr(out), x.shape[-1], C.cast(evs, C.c_void_p), len(events), _MODE[mode], None))
+        return out
+
     def process_bands(self, x, mode="exact"):
         """Per-band outputs only (no sum)."""
         x = np.ascontiguousarray(x, dtype=self.dtype)

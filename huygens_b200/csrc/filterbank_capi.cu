@@ -297,6 +297,37 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
     return HG_OK;
 }
 
+hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t L, const hg_fb_event* events,
+                               size_t n_events, int mode, void* cuda_stream) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process_events: null handle");
+    if (n_events && !events) return hg::fail(HG_ERR_INVALID, "hg_fb_process_events: null events");
+    if (fb->S != 1) return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process_events: one stream per handle (the segments are sub-blocks of one row)");
+    if (!in || !out_sum) return hg::fail(HG_ERR_INVALID, "hg_fb_process_events: null in/out_sum");
+    const size_t es = hg::dtype_size(fb->dtype);
+    size_t t = 0;
+    int launches = 0;
+    for (size_t e = 0; e <= n_events; e++) {
+        const size_t upto = e < n_events ? events[e].tick : L;
+        if (upto < t || upto > L) return hg::fail(HG_ERR_INVALID, "hg_fb_process_events: event %zu at tick %zu is out of order or past the block", e, upto);
+        if (upto > t) {
+            HG_TRY(hg_fb_process(fb, (const char*)in + t * es, (char*)out_sum + t * es, nullptr, upto - t, mode, HG_DIST_NONE, cuda_stream));
+            launches += fb->last_launches;
+            t = upto;
+        }
+        if (e == n_events) break;
+        const hg_fb_event& ev = events[e];
+        switch (ev.kind) {
+            case HG_EV_COEFFICIENTS: HG_TRY(hg_fb_set_coefficients(fb, ev.n0, ev.count, ev.a, ev.na, ev.b, ev.nb)); break;
+            case HG_EV_BOOST: HG_TRY(hg_fb_set_boost(fb, ev.n0, ev.count, ev.a)); break;
+            case HG_EV_MIX: HG_TRY(hg_fb_set_mix(fb, ev.n0, ev.count, ev.a)); break;
+            case HG_EV_OPEN: HG_TRY(hg_fb_open(fb)); break;
+            default: return hg::fail(HG_ERR_INVALID, "hg_fb_process_events: bad event kind %d", ev.kind);
+        }
+    }
+    fb->last_launches = launches;
+    return HG_OK;
+}
+
 hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode) {
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: null handle");
     if (mode != HG_ENV_RING && mode != HG_ENV_REPLICA) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: bad mode %d", mode);

@@ -89,6 +89,10 @@ public:
     // new: process() + one RMSbank(width) envelope follower per band (src/rmsbank.h:54-74 applied to every
     // output of compute()), fused; env[(s * rows + r) * N + n] is the follower of band n after block sample
     // (r+1)*hop - 1, rows = L / hop.  The follower state persists across calls like the filters' own.
+    // new: a block with setter calls at exact ticks (audio-rate modulation); see hg_fb_event in huygens_cuda.h
+    void process(const T* in, T* out_sum, size_t L, const std::vector<hg_fb_event>& events, int mode = HG_MODE_EXACT, void* cuda_stream = nullptr) {
+        hg_check(hg_fb_process_events(fb, in, out_sum, L, events.data(), events.size(), mode, cuda_stream));
+    }
     // follower_mode(HG_ENV_REPLICA) before the first process_env: no ring, ~2x faster, parameters must stay fixed
     void follower_mode(int mode) { hg_check(hg_fb_set_follower_mode(fb, mode)); }
     void process_env(const T* in, T* out_sum, T* env, size_t L, int width = SR / 20, int hop = 64, void* cuda_stream = nullptr) {

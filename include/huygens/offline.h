@@ -56,5 +56,60 @@ template <typename S> std::vector<S> chirp(size_t L, double f0 = 20.0, double f1
     return x;
 }
 
+// ---- on-disk audio for the harness (the reference has no file I/O at all: src/audio.h is PortAudio only) ----
+// read_audio: mono float samples from a raw little-endian float32 file (any other extension) or a RIFF/WAVE
+// file (.wav: PCM 16-bit or IEEE float 32-bit; the first channel of interleaved data).  Returns the sample
+// rate through `rate` (raw files: unchanged).
+inline std::vector<float> read_audio(const std::string& path, int* rate = nullptr) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("read_audio: cannot open " + path);
+    std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const bool wav = path.size() > 4 && path.compare(path.size() - 4, 4, ".wav") == 0;
+    std::vector<float> x;
+    if (!wav) {
+        x.resize(bytes.size() / sizeof(float));
+        std::memcpy(x.data(), bytes.data(), x.size() * sizeof(float));
+        return x;
+    }
+    auto u16 = [&](size_t o) { return (unsigned)(unsigned char)bytes[o] | ((unsigned)(unsigned char)bytes[o + 1] << 8); };
+    auto u32 = [&](size_t o) { return u16(o) | (u16(o + 2) << 16); };
+    if (bytes.size() < 12 || std::memcmp(bytes.data(), "RIFF", 4) || std::memcmp(bytes.data() + 8, "WAVE", 4))
+        throw std::runtime_error("read_audio: not a RIFF/WAVE file: " + path);
+    unsigned fmt = 0, channels = 1, bits = 16;
+    for (size_t o = 12; o + 8 <= bytes.size();) {
+        const unsigned len = u32(o + 4);
+        if (!std::memcmp(bytes.data() + o, "fmt ", 4)) { fmt = u16(o + 8); channels = u16(o + 10); if (rate) *rate = (int)u32(o + 12); bits = u16(o + 22); }
+        else if (!std::memcmp(bytes.data() + o, "data", 4)) {
+            const size_t n = std::min<size_t>(len, bytes.size() - o - 8), frame = (size_t)channels * bits / 8;
+            if (!frame || !((fmt == 1 && bits == 16) || (fmt == 3 && bits == 32)))
+                throw std::runtime_error("read_audio: only PCM16 and float32 WAVE data are read");
+            x.resize(n / frame);
+            for (size_t i = 0; i < x.size(); i++) {
+                const size_t p = o + 8 + i * frame;
+                if (fmt == 1) x[i] = (float)(short)u16(p) / 32768.0f;
+                else { unsigned v = u32(p); std::memcpy(&x[i], &v, 4); }
+            }
+            return x;
+        }
+        o += 8 + len + (len & 1);
+    }
+    throw std::runtime_error("read_audio: no data chunk in " + path);
+}
+// write_audio: ".wav" => mono IEEE-float32 RIFF/WAVE at `rate`; anything else => raw float32
+inline void write_audio(const std::string& path, const std::vector<float>& x, int rate = SR) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("write_audio: cannot open " + path);
+    const bool wav = path.size() > 4 && path.compare(path.size() - 4, 4, ".wav") == 0;
+    if (wav) {
+        auto put32 = [&](unsigned v) { char b[4] = {(char)v, (char)(v >> 8), (char)(v >> 16), (char)(v >> 24)}; f.write(b, 4); };
+        auto put16 = [&](unsigned v) { char b[2] = {(char)v, (char)(v >> 8)}; f.write(b, 2); };
+        const unsigned data = (unsigned)(x.size() * sizeof(float));
+        f.write("RIFF", 4); put32(36 + data); f.write("WAVE", 4);
+        f.write("fmt ", 4); put32(16); put16(3); put16(1); put32((unsigned)rate); put32((unsigned)rate * 4); put16(4); put16(32);
+        f.write("data", 4); put32(data);
+    }
+    f.write(reinterpret_cast<const char*>(x.data()), (std::streamsize)(x.size() * sizeof(float)));
+}
+
 }  // namespace soundmath
 #endif

@@ -91,6 +91,22 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
  * [n_streams][L/hop][n_filters] receives env at block samples hop-1, 2*hop-1, ...; the follower state
  * (running sums and the ring of the last `width` squares) persists in the handle; width >= 64 and
  * fixed at the first call.  Bit-identical to Filterbank bands -> RMSbank. */
+/* new: a block with parameter changes at exact ticks — the reference's setter calls between two ticks of the
+ * caller loop (audio-rate modulation, src/subtractive.h:215-230: coefficients() + mix() every tick).  Event e
+ * takes effect before tick events[e].tick of this block (ticks ascending, <= L); the block is rendered
+ * in segments between events, so results equal per-tick setter calls bit for bit.  n_streams must be 1. */
+enum { HG_EV_COEFFICIENTS = 0, HG_EV_BOOST = 1, HG_EV_MIX = 2, HG_EV_OPEN = 3 };
+typedef struct {
+    size_t tick;
+    int kind;            /* HG_EV_* */
+    int n0, count;       /* filters [n0, n0 + count) */
+    const void* a;       /* COEFFICIENTS: forward [count][na];  BOOST / MIX: values [count] */
+    int na;
+    const void* b;       /* COEFFICIENTS: back [count][nb] */
+    int nb;
+} hg_fb_event;
+hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t L, const hg_fb_event* events,
+                               size_t n_events, int mode, void* cuda_stream);
 /* How the followers obtain y[t-width].  HG_ENV_RING (default): a ring of the last `width` squares per filter
  * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter); follows
  * parameter changes.  HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same

@@ -49,6 +49,31 @@ def test_render_harness_matches_oracle(harness, tmp_path, flags, dtype, oracle_l
     assert rel_err(got, ref.astype(np.float32)) <= 2e-6
 
 
+def test_render_harness_reads_and_writes_audio_files(harness, tmp_path, oracle_lib):
+    """the harness renders from a WAV (PCM16) or raw float32 file and writes float32 WAV."""
+    import struct
+    import wave
+    N, L = 32, 6000
+    x16 = (design.white_noise(L) * 20000).astype(np.int16)
+    with wave.open(str(tmp_path / "in.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(48000); w.writeframes(x16.tobytes())
+    out = tmp_path / "out.wav"
+    r = subprocess.run([os.path.join(harness, "render"), "--filters", str(N), "--double", "--in", str(tmp_path / "in.wav"),
+                        "--out", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = out.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE" and struct.unpack("<H", raw[20:22])[0] == 3      # IEEE float
+    got = np.frombuffer(raw[44:], dtype=np.float32)
+    x = (x16.astype(np.float32) / 32768.0)
+    ref = _resynthesis_oracle(N, np.float64, x)
+    assert len(got) == L and rel_err(got, ref.astype(np.float32)) <= 2e-6
+    x.tofile(tmp_path / "in.f32")
+    r = subprocess.run([os.path.join(harness, "render"), "--filters", str(N), "--double", "--in", str(tmp_path / "in.f32"),
+                        "--out", str(tmp_path / "out.f32")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(tmp_path / "out.f32", dtype=np.float32), got)
+
+
 def test_render_harness_c1_full(harness, tmp_path, oracle_lib):
     """BASELINE configs[0]: Filterbank<double>, 64 resonant band-passes, 10 s of 48 kHz white noise."""
     out = tmp_path / "c1.f32"
