@@ -166,6 +166,8 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     fb->cur_dist = distortion;
     fb->last_launches = 0;
     if (L == 0) return HG_OK;
+    if (fb->env_mode == HG_ENV_REPLICA && fb->d_rms_sum && !fb->cur_env)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_process: replica followers are running and must see every tick; render through hg_fb_process_env");
     if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
     if (!out_sum && !out_bands) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
     HG_CUDA(cudaSetDevice(fb->device));
