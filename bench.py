@@ -42,6 +42,9 @@ WORKLOADS = {
     "c3_16384": dict(N=16384, seconds=10, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
     # BASELINE configs[3] without the envelope followers: 1024 independent streams x 1024 filters, 1 s blocks
     "c4": dict(N=1024, streams=1024, seconds=1, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="white"),
+    # BASELINE configs[4]: 65,536 sinusoid partials driven by Filterbank/RMSbank analysis of the input, 60 s
+    # (run_c5: analysis bank + fused followers -> envelope rows -> Oscbank amplitudes; --strong splits the partials)
+    "c5": dict(N=65536, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
 }
 
 
@@ -220,6 +223,102 @@ def run_reference(args, w, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c5(args, w, rank, world, local):
+    """BASELINE configs[4]: Oscbank additive synthesis driven by analysis envelopes.  One step = the whole block:
+    Filterbank(N) with one RMSbank(2400) follower per band (hop 64, replica followers) -> envelope rows ->
+    Oscbank(N) with one amplitude row per hop -> mixed output; ranks hold N filters + N partials each and
+    reduce the mix once per block.  Unit: partial-samples/s (a partial-sample includes its analysis band)."""
+    import torch
+    import torch.distributed as dist
+    import huygens_b200 as hb
+    from huygens_b200 import design
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, L, hop = w["N"], int(w["seconds"] * SR), 64
+    fb = make_bank(hb.Filterbank, w, rank, world, np.float32, arith=args.arith, device=local)
+    from huygens_b200.sharding import filter_range
+    lo, hi = filter_range(N * world, rank, world)
+    freqs = design.log_spaced(N * world, w["f_lo"], w["f_hi"])[lo:hi]
+    osc = hb.Oscbank(N, dtype=np.float32, arith=args.arith, device=local)
+    osc.set_frequencies(freqs)
+    osc.open()
+    x = torch.from_numpy(synth_input(w, L, np.float32)).cuda()
+    out = torch.empty_like(x)
+    env = torch.empty((1, L // hop, N), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peak = hb.fma_peak(np.float32, device=local)
+    mix = [None]
+
+    def step():
+        fb.process_env(x, width=2400, hop=hop, out=out, env=env, followers="replica")
+        mix[0] = osc.process((L // hop) * hop, amps=env[0], hop=hop, want_mix=False, device_out=True)
+        if world > 1:
+            dist.reduce(mix[0], dst=0, op=dist.ReduceOp.SUM)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        fb.process_env(x, width=2400, hop=hop, out=out, env=env, followers="replica")
+        ev[i][1].record()
+        mix[0] = osc.process((L // hop) * hop, amps=env[0], hop=hop, want_mix=False, device_out=True)
+        if world > 1:
+            dist.reduce(mix[0], dst=0, op=dist.ReduceOp.SUM)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_an = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
+    t_all = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_all, t_an], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_all, t_an = tt.tolist()
+    # end to end: host input in, mixed audio out (the envelope rows never leave the device)
+    xh = x.cpu().pin_memory().numpy()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fb.process_env(xh, width=2400, hop=hop, env=env, followers="replica")
+        m = osc.process((L // hop) * hop, amps=env[0], hop=hop, want_mix=False, device_out=True)
+        m_host = m.cpu()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    units = float(N) * world * L * args.steps
+    slots = SLOTS_PER_FILTER_SAMPLE + 3 + 11            # band filter + follower + phasor tick (9 slots + 2 divisions, SURVEY 8d)
+    per_gpu = float(N) * L * args.steps / t_all
+    line = {
+        "metric": "partial-samples/s (analysis band + follower + Oscbank partial)", "value": units / t_all, "unit": "partial-samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_all / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{N} analysis biquads + RMSbank(2400) followers -> {N} Oscbank partials per GPU, {w['seconds']} s 48 kHz chirp, hop 64",
+                   "partials_total": N * world, "samples": L, "partition": "filters/partials" if world > 1 else "none",
+                   "arith": args.arith, "l2": "flushed between steps (256 MiB write)"},
+        "e2e": {"value": units / t_e2e, "unit": "partial-samples/s", "h2d_bytes_per_step": int(L * 4), "d2h_bytes_per_step": int(m_host.numel() * 4)},
+        "gpu_launches": None, "clocks": clocks,
+        "roofline": {"bound": "fp32_fma", "achieved": per_gpu * slots / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
+                     "frac": per_gpu * slots / peak["slots_per_s"], "traffic": None, "slots_per_unit": slots,
+                     "analysis_ms": t_an / args.steps * 1e3, "synthesis_ms": (t_all - t_an) / args.steps * 1e3,
+                     "peak_source": "hg_fma_peak FFMA microbenchmark, measured in this run"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_config(w, args, world):
     tname = "double" if w.get("dtype") == "f64" else "float"
     sname = f"{w['streams']} streams x " if w.get("streams", 1) > 1 else ""
@@ -245,6 +344,9 @@ def main():
         w["N"] //= world
     if args.impl == "reference":
         run_reference(args, w, rank, world)
+        return
+    if args.workload == "c5":
+        run_c5(args, w, rank, world, local)
         return
 
     import torch
