@@ -146,8 +146,9 @@ __device__ __forceinline__ void ru_tile(const T* __restrict__ xc, T* __restrict_
 // ENV == 2: a full tile of the filter AND of its `width`-lagged replica, interleaved (two independent
 // dependency chains per lane), with the envelope follower folded in: q = y^2, q_old = (replica y)^2,
 // S <- (q - q_old) + S  (rmsbank.h:58-61; the "+ 0*0" of a real sample's |z|^2 is exact for q >= 0 and dropped).
-// S after tick `je` of the tile (if 0 <= je < TILE) is returned in s_at_je for the envelope row.
-template <typename T, bool FMA, int TAPS>
+// CAP: S after tick `je` of the tile (0 <= je < TILE) is captured in s_at_je for the envelope row; without CAP
+// the caller takes S at the end of the tile (rows that fall on tile ends, e.g. hop = 64 on aligned blocks).
+template <typename T, bool FMA, int TAPS, bool CAP>
 __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* __restrict__ xlc, T* __restrict__ yrow,
                                             T b0, T b1, T b2, T a1, T a2, T p, T pl,
                                             T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2,
@@ -167,7 +168,7 @@ __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* _
             yy[j] = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
             const T yl = ru_sample<T, FMA, TAPS>(xlq[q & 1][j], b0, b1, b2, a1, a2, pl, y1l, y2l, x1l, x2l, m1l, m2l, t2l);
             rsum = A::add(A::sub(A::mul(yy[j], yy[j]), A::mul(yl, yl)), rsum);
-            if (4 * q + j == je) s_at_je = rsum;
+            if (CAP && 4 * q + j == je) s_at_je = rsum;
         }
         st4<T>(yrow + 4 * q, yy);
     }
@@ -312,9 +313,17 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 const T* xlc = xls + xb * XT + kc * TILE;
                 const int je = hop_left <= TILE ? (int)hop_left - 1 : -1;
                 T s_je = (T)0;
-                if (taps == 2) ru_tile_env<T, FMA, 2>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                else if (taps == 1) ru_tile_env<T, FMA, 1>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                else ru_tile_env<T, FMA, 0>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                if (je < 0 || je == TILE - 1) {
+                    // no row, or the row falls on the tile's last tick: S at the end of the tile is what is needed
+                    if (taps == 2) ru_tile_env<T, FMA, 2, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    s_je = rsum;
+                } else {
+                    if (taps == 2) ru_tile_env<T, FMA, 2, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                }
                 if (je >= 0) {
                     if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(s_je, wT));   // rmsbank.h:64
                     env_row++;
