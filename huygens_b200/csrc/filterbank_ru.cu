@@ -300,7 +300,30 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 qo[j] = (j < cnt0) ? ring[(size_t)pj * 32] : (T)0;
             }
         }
+        static_assert(NB == 2, "the steady-state loop toggles between two tile slots");
         for (int k = 0; k < ntiles; k++) {
+            if (ENV == 0 && conv && kc == 0 && (long)(k + TPC) * TILE <= L) {
+                // steady state: a whole input chunk of full tiles with converged smoothers.  Nothing but the two
+                // hand-over barriers per tile around the unrolled recurrence (the general path below spends ~75
+                // instructions per tile on cases that cannot occur here).
+                mbar_wait(&x_full[xb], xpar);
+                const T* xcb = xs + xb * XT;
+#define HG_RU_CHUNK(TP)                                                                                          \
+                _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
+                    mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
+                    ru_tile<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2); \
+                    __syncwarp();                                                                               \
+                    if (lane == 0) mbar_arrive(&yf[yb]);                                                        \
+                    ypar ^= (unsigned)yb;                                                                       \
+                    yb ^= 1;                                                                                    \
+                }
+                if (taps == 2) { HG_RU_CHUNK(2) } else if (taps == 1) { HG_RU_CHUNK(1) } else { HG_RU_CHUNK(0) }
+#undef HG_RU_CHUNK
+                if (lane == 0) mbar_arrive(&x_empty[xb]);
+                if (++xb == XB) { xb = 0; xpar ^= 1u; }
+                k += TPC - 1;
+                continue;
+            }
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
             if (kc == 0) mbar_wait(&x_full[xb], xpar);
             mbar_wait(&ye[yb], ypar ^ 1u);
