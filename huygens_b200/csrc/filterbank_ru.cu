@@ -324,6 +324,37 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 k += TPC - 1;
                 continue;
             }
+            if (ENV == 2 && conv && convl && kc == 0 && lag_left == 0 && !was_idle && (long)(k + TPC) * TILE <= L &&
+                Q.hop % TILE == 0 && hop_left % TILE == 0) {
+                // the same steady state with replica followers: filter + replica + follower per tile, envelope rows
+                // on tile ends
+                mbar_wait(&x_full[xb], xpar);
+                const T* xcb = xs + xb * XT;
+                const T* xlcb = xls + xb * XT;
+#define HG_RU_CHUNK_ENV(TP)                                                                                      \
+                _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
+                    mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
+                    T unused = (T)0;                                                                            \
+                    ru_tile_env<T, FMA, TP, false>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, pl, \
+                                                   y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, -1, unused); \
+                    hop_left -= TILE;                                                                           \
+                    if (hop_left == 0) {                                                                        \
+                        if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(rsum, wT)); \
+                        env_row++;                                                                              \
+                        hop_left = Q.hop;                                                                       \
+                    }                                                                                           \
+                    __syncwarp();                                                                               \
+                    if (lane == 0) mbar_arrive(&yf[yb]);                                                        \
+                    ypar ^= (unsigned)yb;                                                                       \
+                    yb ^= 1;                                                                                    \
+                }
+                if (taps == 2) { HG_RU_CHUNK_ENV(2) } else if (taps == 1) { HG_RU_CHUNK_ENV(1) } else { HG_RU_CHUNK_ENV(0) }
+#undef HG_RU_CHUNK_ENV
+                if (lane == 0) mbar_arrive(&x_empty[xb]);
+                if (++xb == XB) { xb = 0; xpar ^= 1u; }
+                k += TPC - 1;
+                continue;
+            }
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
             if (kc == 0) mbar_wait(&x_full[xb], xpar);
             mbar_wait(&ye[yb], ypar ^ 1u);
