@@ -7,6 +7,7 @@
 #include "../include/huygens/latchbank.h"
 #include "../include/huygens/slidebank.h"
 #include "../include/huygens/stickbank.h"
+#include "../include/huygens/offline.h"
 
 using namespace soundmath;
 
@@ -49,6 +50,34 @@ int main(int argc, char** argv) {
             std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum,
                         ssum.real(), ssum.imag());
             osc.tick(); rms.tick(); rms2.tick(); F.tick(); slide.tick(); smooth.tick();
+        }
+        // block entry points of the drop-in Filterbank: fused envelope followers (replica mode) and a parameter
+        // schedule at exact ticks; printed as "# name value" lines for the pytest check
+        {
+            const int NB = 16, L = 1200, width = 96, hop = 32;
+            Filterbank<double> bank(2, NB, 0.01, 0.05);
+            for (int i = 0; i < NB; i++) bank.coefficients(i, {1.0, 0.0, -1.0}, {-1.9 + 0.05 * i, 0.98});
+            bank.open();
+            bank.boost(std::vector<double>(NB, 1.0));
+            std::vector<double> x = white_noise<double>(L), y(L), env((size_t)(L / hop) * NB);
+            bank.follower_mode(HG_ENV_REPLICA);
+            bank.process_env(x.data(), y.data(), env.data(), L, width, hop);
+            double es = 0, ys = 0;
+            for (double v : env) es += v;
+            for (double v : y) ys += v;
+            std::printf("# env_sum %.17g\n# env_out_sum %.17g\n", es, ys);
+            Filterbank<double> bank2(2, NB, 0.01, 0.05);
+            for (int i = 0; i < NB; i++) bank2.coefficients(i, {1.0, 0.0, -1.0}, {-1.9 + 0.05 * i, 0.98});
+            bank2.open();
+            bank2.boost(std::vector<double>(NB, 1.0));
+            const double half = 0.5;
+            std::vector<hg_fb_event> ev(2);
+            ev[0] = hg_fb_event{300, HG_EV_MIX, 2, 1, &half, 0, nullptr, 0};
+            ev[1] = hg_fb_event{700, HG_EV_BOOST, 5, 1, &half, 0, nullptr, 0};
+            bank2.process(x.data(), y.data(), L, ev);
+            ys = 0;
+            for (double v : y) ys += v * v;
+            std::printf("# events_energy %.17g\n", ys);
         }
     } catch (const cuda_error& e) {
         std::fprintf(stderr, "huygens_cuda error %d: %s\n", e.status, e.what());

@@ -3,8 +3,15 @@
 // callback convention (audio.h:18,139-148), synthetic input buffers instead of a sound card.
 #ifndef HUYGENS_B200_OFFLINE_H
 #define HUYGENS_B200_OFFLINE_H
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <stdexcept>
+#include <string>
+#include <vector>
 #include "includes.h"
 
 namespace soundmath {

@@ -89,8 +89,33 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
     ticks = 80
     r = subprocess.run([os.path.join(harness, "banks_demo"), str(ticks)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+    lines = r.stdout.strip().splitlines()
+    extra = {ln.split()[1]: float(ln.split()[2]) for ln in lines if ln.startswith("#")}
+    got = np.array([[float(v) for v in line.split()] for line in lines if not line.startswith("#")])
     assert got.shape == (ticks, 9)
+    # the block entry points of the drop-in header: fused followers (replica mode) and a parameter schedule
+    NB, L, width, hop = 16, 1200, 96, 32
+
+    def mk():
+        fb = oracle.Filterbank(2, NB, 0.01, 0.05)
+        for i in range(NB):
+            fb.coefficients(i, [1.0, 0.0, -1.0], [-1.9 + 0.05 * i, 0.98])
+        fb.open()
+        fb.boost(np.ones(NB))
+        return fb
+    x = design.white_noise(L)
+    ys, bands = mk().process(x, bands=True)
+    env = oracle.RMSbank(NB, width).process(bands)[:, hop - 1::hop][:, : L // hop]
+    assert abs(extra["env_sum"] - env.sum()) <= 1e-12 * abs(env.sum())
+    assert abs(extra["env_out_sum"] - ys.sum()) <= 1e-12 * np.abs(ys).sum()
+    fb = mk()
+    y = [fb.process(x[:300])]
+    fb.mix(2, 0.5)
+    y.append(fb.process(x[300:700]))
+    fb.boost(5, 0.5)
+    y.append(fb.process(x[700:]))
+    e = float((np.concatenate(y) ** 2).sum())
+    assert abs(extra["events_energy"] - e) <= 1e-12 * e
     osc = oracle.Oscbank(8)
     for i in range(8):
         osc.freqmod(i, 110.0 * (i + 1))
