@@ -9,13 +9,15 @@
 // unpinned: tests/build.sh:8 only passes -I /opt/homebrew/include/eigen3) and the reference
 // ships no golden vectors, assertions or expected outputs.  The restatement is
 // pinned two ways: (1) closed-form known-answer tests (tests/test_oracle_kat.py); (2)
-// oracle/_ref — the UNMODIFIED reference headers src/{filterbank,oscbank,rmsbank,
-// multichannel}.h compiled where they lie against a minimal Eigen/PortAudio/RtMidi shim
+// oracle/_ref — the UNMODIFIED reference headers src/{filterbank,oscbank,rmsbank,latchbank,
+// slidebank,stickbank,multichannel}.h compiled where they lie against a minimal Eigen/PortAudio/RtMidi shim
 // (oracle/shim/, ours) — must agree with this file bit-for-bit on seeded inputs
 // (tests/test_oracle_vs_ref.py).  Because the shim is not Eigen itself, Eigen's internal
 // summation orders stay unverified => "parity unpinned" at the last-ulp level of (a) the 3-tap
-// GEMV when b1 != 0 and (b) the N-way mixdown dot.  Every caller in the reference uses
-// b = {b0, 0, -b0}, for which (a) is order-independent.
+// GEMV when b1 != 0, (b) the N-way mixdown dot, (c) Stickbank's N x order GEMV for order > 1 and
+// (d) the column order of Slidebank's sparse product (two terms per row: same value either way).
+// Every caller in the reference uses b = {b0, 0, -b0} and Stickbank order 1, for which (a) and (c)
+// are order-independent.  tests/golden/*.npz hold _ref outputs so the pin also holds on the GPU box.
 //
 // Arithmetic modes (template parameter FMA):
 //   strict (FMA=false): every multiply and add rounded separately.  This is what
