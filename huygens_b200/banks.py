@@ -140,7 +140,8 @@ class Filterbank(_Handle):
     def process_env(self, x, width=2400, hop=64, out=None, env=None, followers=None):
         """Block render + one RMSbank(width) envelope follower per (stream, filter), fused on the device.
         Returns (out_sum, env[streams][L // hop][N]); env rows are block samples hop-1, 2*hop-1, ...
-        followers = "ring" (default) or "replica" (fixed parameters, no ring traffic), at the first call."""
+        followers = "ring" (default) or "replica" (no ring traffic, ~2x faster; every tick must then be rendered
+        through process_env), chosen at the first call."""
         if followers is not None:
             L.check(L.lib().hg_fb_set_follower_mode(self._h, {"ring": 1, "replica": 2}[followers]))
         if _is_torch(x):

@@ -355,8 +355,23 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         HG_CUDA(cudaMemcpy2DAsync(fb->xcat.p, pitch * sizeof(T), fb->d_xhist, H * sizeof(T), H * sizeof(T), fb->S, cudaMemcpyDeviceToDevice, st));
         HG_CUDA(cudaMemcpy2DAsync((T*)fb->xcat.p + H, pitch * sizeof(T), d_in, L * sizeof(T), L * sizeof(T), fb->S, cudaMemcpyDeviceToDevice, st));
     }
-    for (size_t t0 = 0; t0 < L; t0 += seg) {
-        const size_t len = (L - t0 < seg) ? (L - t0) : seg;
+    size_t len = 0;
+    for (size_t t0 = 0; t0 < L; t0 += len) {
+        len = (L - t0 < seg) ? (L - t0) : seg;
+        if (replica) {
+            // parameter sets reach the replicas `width` ticks after the filters: hand over the ones that are due,
+            // and end this segment where the next one becomes due
+            const long long now = fb->rms_ticks + (long long)t0;
+            while (!fb->lag_pending.empty() && fb->lag_pending.front().tick <= now) {
+                const hg_fb::LagPending& pe = fb->lag_pending.front();
+                HG_CUDA(cudaMemcpyAsync(fb->d_lag_par, pe.par.data(), pe.par.size(), cudaMemcpyHostToDevice, st));
+                HG_CUDA(cudaStreamSynchronize(st));          // pageable source: let the copy land before the set is dropped
+                fb->lag_taps = pe.taps;
+                fb->lag_pending.pop_front();
+            }
+            if (!fb->lag_pending.empty() && fb->lag_pending.front().tick < now + (long long)len)
+                len = (size_t)(fb->lag_pending.front().tick - now);
+        }
         FbK1Params<T> P;
         P.par = (const T*)fb->d_par;
         P.state = (T*)fb->d_state;
@@ -390,7 +405,10 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
                 E.env = (T*)fb->cur_env_out; E.rms_sum = (T*)fb->d_rms_sum; E.rms_ring = (T*)fb->d_rms_ring;
                 E.width = fb->rms_width; E.hop = fb->cur_hop; E.env_rows = (long)fb->cur_env_rows;
                 E.t_base = (long)t0; E.tick0 = fb->rms_ticks;
-                if (replica) { E.in_lag = (const T*)fb->xcat.p + 4 + t0; E.lag_stride = (long)pitch; E.lag_state = (T*)fb->d_lag_state; }
+                if (replica) {
+                    E.in_lag = (const T*)fb->xcat.p + 4 + t0; E.lag_stride = (long)pitch; E.lag_state = (T*)fb->d_lag_state;
+                    E.lag_par = (const T*)fb->d_lag_par; E.lag_taps = fb->lag_taps;
+                }
             }
             rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st, fb->cur_env ? &E : nullptr);
         }

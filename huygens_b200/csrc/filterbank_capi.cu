@@ -105,6 +105,7 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);
     if (fb->d_rms_ring) cudaFree(fb->d_rms_ring);
     if (fb->d_lag_state) cudaFree(fb->d_lag_state);
+    if (fb->d_lag_par) cudaFree(fb->d_lag_par);
     if (fb->d_xhist) cudaFree(fb->d_xhist);
     fb->xcat.release();
     delete fb;
@@ -190,6 +191,19 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
         // the pinned shadow may be rewritten by a setter right after we return
         HG_CUDA(cudaStreamSynchronize(st));
         fb->dirty = false;
+        // replica followers replay the filters `width` ticks late: the new set reaches them that much later
+        if (fb->env_mode == HG_ENV_REPLICA && fb->lag_live) {
+            hg_fb::LagPending pe;
+            pe.tick = fb->rms_ticks + fb->rms_width;
+            pe.taps = fb->taps;
+            pe.par.assign((const unsigned char*)fb->h_par, (const unsigned char*)fb->h_par + 7 * N * es);
+            fb->lag_pending.push_back(std::move(pe));
+        }
+    }
+    if (fb->env_mode == HG_ENV_REPLICA && fb->cur_env && fb->d_lag_par && !fb->lag_live) {
+        HG_CUDA(cudaMemcpyAsync(fb->d_lag_par, fb->d_par, 7 * N * es, cudaMemcpyDeviceToDevice, st));
+        fb->lag_taps = fb->taps;
+        fb->lag_live = true;
     }
     const bool in_dev = hg::is_device_ptr(in);
     const bool out_dev = out_sum ? hg::is_device_ptr(out_sum) : true;
@@ -251,8 +265,6 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
     HG_CUDA(cudaSetDevice(fb->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t es = hg::dtype_size(fb->dtype), S = fb->S, N = fb->N;
-    if (fb->env_mode == 2 && fb->dirty && fb->d_rms_sum)
-        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process_env: replica followers replay the filters %d ticks late and cannot follow a parameter change; use HG_ENV_RING", width);
     if (!fb->d_rms_sum) {
         // RMSbank(width) per (stream, filter): running sums zeroed (rmsbank.h:34-44) and either the ring of the
         // last `width` squares (zeroed) or the lagged replicas (state of the filters now, idle for `width` ticks)
@@ -263,6 +275,7 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
         if (fb->env_mode == 2) {
             const size_t H = (size_t)width + 4;
             if ((ce = cudaMalloc(&fb->d_lag_state, 3 * S * N * es)) != cudaSuccess ||
+                (ce = cudaMalloc(&fb->d_lag_par, 7 * N * es)) != cudaSuccess ||
                 (ce = cudaMalloc(&fb->d_xhist, S * H * es)) != cudaSuccess)
                 return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: replica state: %s", cudaGetErrorString(ce));
             HG_CUDA(cudaMemcpyAsync(fb->d_lag_state, fb->d_state, 3 * S * N * es, cudaMemcpyDeviceToDevice, st));

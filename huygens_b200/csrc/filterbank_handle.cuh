@@ -1,6 +1,8 @@
 // filterbank_handle.cuh — hg_fb handle layout and kernel parameter blocks.
 #pragma once
 #include <cstdint>
+#include <deque>
+#include <vector>
 #include "hg_common.cuh"
 
 constexpr int K1_NT = 128;   // threads per CTA of the exact kernel (one warp per SM sub-partition)
@@ -40,6 +42,11 @@ struct hg_fb {
     int env_mode = 1;            // HG_ENV_RING (1) or HG_ENV_REPLICA (2), fixed once the followers have started
     void* d_lag_state = nullptr; // replica followers: [3][S][N] y1, y2, p of the lagged copies
     void* d_xhist = nullptr;     // replica followers: [S][width + 4] input samples before the current block
+    void* d_lag_par = nullptr;   // replica followers: [7][N] parameters the replicas currently run with
+    int lag_taps = 0;
+    bool lag_live = false;       // d_lag_par holds a parameter set (from the first block with followers on)
+    struct LagPending { long long tick; int taps; std::vector<unsigned char> par; };
+    std::deque<LagPending> lag_pending;   // parameter sets on their way to the replicas: active from global tick `tick`
     hg::DevBuf xcat;             // replica followers: [S][width + 4 + L] history + block
     int* d_sm_slot = nullptr;        // per-SM CTA arrival counters (role rotation of co-resident ws CTAs)
     hg::DevBuf env_stage;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
@@ -80,6 +87,8 @@ template <typename T> struct FbEnvArgs {
     const T* in_lag = nullptr;    // replica followers: lagged input of this launch (null => ring followers)
     long lag_stride = 0;
     T* lag_state = nullptr;
+    const T* lag_par = nullptr;   // the replicas' parameter set [7][N] and its tap structure
+    int lag_taps = 0;
 };
 template <typename T>
 hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st,

@@ -150,7 +150,7 @@ __device__ __forceinline__ void ru_tile(const T* __restrict__ xc, T* __restrict_
 // the caller takes S at the end of the tile (rows that fall on tile ends, e.g. hop = 64 on aligned blocks).
 template <typename T, bool FMA, int TAPS, bool CAP>
 __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* __restrict__ xlc, T* __restrict__ yrow,
-                                            T b0, T b1, T b2, T a1, T a2, T p, T pl,
+                                            T b0, T b1, T b2, T a1, T a2, T p, T b0l, T b1l, T b2l, T a1l, T a2l, T pl,
                                             T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2,
                                             T& y1l, T& y2l, T& x1l, T& x2l, T& m1l, T& m2l, T& t2l,
                                             T& rsum, int je, T& s_at_je) {
@@ -166,7 +166,7 @@ __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* _
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             yy[j] = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
-            const T yl = ru_sample<T, FMA, TAPS>(xlq[q & 1][j], b0, b1, b2, a1, a2, pl, y1l, y2l, x1l, x2l, m1l, m2l, t2l);
+            const T yl = ru_sample<T, FMA, TAPS>(xlq[q & 1][j], b0l, b1l, b2l, a1l, a2l, pl, y1l, y2l, x1l, x2l, m1l, m2l, t2l);
             rsum = A::add(A::sub(A::mul(yy[j], yy[j]), A::mul(yl, yl)), rsum);
             if (CAP && 4 * q + j == je) s_at_je = rsum;
         }
@@ -192,6 +192,8 @@ template <typename T> struct FbRuParams {
     const T* in_lag;      // per stream: in_lag[t] = x[t - width] for launch-relative t (t = -1, -2 valid)
     long lag_stride;
     T* lag_state;         // [3][S][N]: y1, y2, p of the replicas
+    const T* lag_par;     // [7][N] the parameters the replicas run with: what the filters ran with `width` ticks ago
+    int lag_taps;         // tap structure of lag_par
 };
 
 // ENV: 0 no followers; 1 followers with the ring of y^2 in HBM; 2 followers with lagged replicas
@@ -276,14 +278,23 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         bool convl = false, was_idle = false;
         long lag_left = 0;
         const T* inl = nullptr;
+        // the replicas' own parameter set: a change reaches them `width` ticks after it reached the filters
+        T b0l = b0, b1l = b1, b2l = b2, a1l = a1, a2l = a2, cpl = cp;
+        int tapsl = taps;
         if (ENV == 2) {
-            if (ok) { y1l = Q.lag_state[0 * SN + si]; y2l = Q.lag_state[1 * SN + si]; pl = Q.lag_state[2 * SN + si]; }
+            if (ok) {
+                y1l = Q.lag_state[0 * SN + si]; y2l = Q.lag_state[1 * SN + si]; pl = Q.lag_state[2 * SN + si];
+                b0l = Q.lag_par[0 * (size_t)N + n]; b1l = Q.lag_par[1 * (size_t)N + n]; b2l = Q.lag_par[2 * (size_t)N + n];
+                a1l = Q.lag_par[3 * (size_t)N + n]; a2l = Q.lag_par[4 * (size_t)N + n];
+                cpl = A::mul(P.c_p, Q.lag_par[5 * (size_t)N + n]);
+            }
+            tapsl = Q.lag_taps;
             inl = Q.in_lag + (size_t)s * Q.lag_stride;
             const long long started = Q.tick0 + Q.t_base - Q.width;      // replica ticks already done (< 0: idle)
             lag_left = started < 0 ? (long)(-started) : 0;
             x1l = inl[-1]; x2l = inl[-2];
-            m1l = A::mul(b0, x1l); m2l = A::mul(b0, x2l); t2l = A::mul(a2, y2l);
-            convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+            m1l = A::mul(b0l, x1l); m2l = A::mul(b0l, x2l); t2l = A::mul(a2l, y2l);
+            convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cpl) == pl);
         }
         long hop_left = ENV ? (long)Q.hop - (Q.t_base % Q.hop) : 0;        // samples until the next envelope row
         long env_row = ENV ? Q.t_base / Q.hop : 0;
@@ -324,7 +335,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 k += TPC - 1;
                 continue;
             }
-            if (ENV == 2 && conv && convl && kc == 0 && lag_left == 0 && !was_idle && (long)(k + TPC) * TILE <= L &&
+            if (ENV == 2 && conv && convl && taps == tapsl && kc == 0 && lag_left == 0 && !was_idle && (long)(k + TPC) * TILE <= L &&
                 Q.hop % TILE == 0 && hop_left % TILE == 0) {
                 // the same steady state with replica followers: filter + replica + follower per tile, envelope rows
                 // on tile ends
@@ -335,7 +346,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
                     mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
                     T unused = (T)0;                                                                            \
-                    ru_tile_env<T, FMA, TP, false>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, pl, \
+                    ru_tile_env<T, FMA, TP, false>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, \
                                                    y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, -1, unused); \
                     hop_left -= TILE;                                                                           \
                     if (hop_left == 0) {                                                                        \
@@ -362,21 +373,21 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             T* yrow = ybase + yb * 32 * RS;
             int tt = 0;
             bool fused = false;
-            if (ENV == 2 && conv && convl && lag_left == 0 && !was_idle && tn == TILE && Q.hop >= TILE) {
+            if (ENV == 2 && conv && convl && taps == tapsl && lag_left == 0 && !was_idle && tn == TILE && Q.hop >= TILE) {
                 // filter + replica + follower in one unrolled tile
                 const T* xlc = xls + xb * XT + kc * TILE;
                 const int je = hop_left <= TILE ? (int)hop_left - 1 : -1;
                 T s_je = (T)0;
                 if (je < 0 || je == TILE - 1) {
                     // no row, or the row falls on the tile's last tick: S at the end of the tile is what is needed
-                    if (taps == 2) ru_tile_env<T, FMA, 2, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else if (taps == 1) ru_tile_env<T, FMA, 1, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else ru_tile_env<T, FMA, 0, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    if (taps == 2) ru_tile_env<T, FMA, 2, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
                     s_je = rsum;
                 } else {
-                    if (taps == 2) ru_tile_env<T, FMA, 2, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else if (taps == 1) ru_tile_env<T, FMA, 1, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else ru_tile_env<T, FMA, 0, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    if (taps == 2) ru_tile_env<T, FMA, 2, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
                 }
                 if (je >= 0) {
                     if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(s_je, wT));   // rmsbank.h:64
@@ -425,19 +436,19 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                     // the replica starts in this tile: its input history is what precedes its first sample
                     const long t1 = (long)k * TILE + j0;                          // launch-relative tick of that sample
                     x1l = inl[t1 - 1]; x2l = inl[t1 - 2];
-                    convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+                    convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cpl) == pl);
                     was_idle = false;
                 }
                 for (int j = 0; j < tn; j++) {
                     T yl = (T)0;                                                  // idle: y[t - width] = 0 (rmsbank.h:36-44 setZero)
                     if (j >= j0) {
-                        if (!convl) pl = A::muladd(s_p, pl, cp);
+                        if (!convl) pl = A::muladd(s_p, pl, cpl);
                         const T x0 = xlc[j];
-                        T fw = A::mul(b0, x0);
-                        fw = A::muladd(b1, x1l, fw);
-                        fw = A::muladd(b2, x2l, fw);
-                        T fbk = A::mul(a1, y1l);
-                        fbk = A::muladd(a2, y2l, fbk);
+                        T fw = A::mul(b0l, x0);
+                        fw = A::muladd(b1l, x1l, fw);
+                        fw = A::muladd(b2l, x2l, fw);
+                        T fbk = A::mul(a1l, y1l);
+                        fbk = A::muladd(a2l, y2l, fbk);
                         yl = A::mulsub(fw, pl, fbk);
                         y2l = y1l; y1l = yl;
                         x2l = x1l; x1l = x0;
@@ -450,8 +461,8 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                         hop_left = Q.hop;
                     }
                 }
-                m1l = A::mul(b0, x1l); m2l = A::mul(b0, x2l); t2l = A::mul(a2, y2l);
-                if (!convl && lag_left == 0 && !was_idle) convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cp) == pl);
+                m1l = A::mul(b0l, x1l); m2l = A::mul(b0l, x2l); t2l = A::mul(a2l, y2l);
+                if (!convl && lag_left == 0 && !was_idle) convl = __all_sync(0xffffffffu, A::muladd(s_p, pl, cpl) == pl);
             }
             if (ENV == 1 && ok) {
                 // envelope follower over the tile just rendered (own row of the y tile), rmsbank.h:58-64
@@ -707,11 +718,12 @@ hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W
     FbRuParams<T> Q;
     Q.k = P; Q.W = W; Q.cps = cps;
     Q.env = nullptr; Q.rms_sum = nullptr; Q.rms_ring = nullptr; Q.width = 1; Q.hop = 1; Q.env_rows = 0; Q.t_base = 0; Q.tick0 = 0;
-    Q.in_lag = nullptr; Q.lag_stride = 0; Q.lag_state = nullptr;
+    Q.in_lag = nullptr; Q.lag_stride = 0; Q.lag_state = nullptr; Q.lag_par = nullptr; Q.lag_taps = 0;
     if (env) {
         Q.env = env->env; Q.rms_sum = env->rms_sum; Q.rms_ring = env->rms_ring; Q.width = env->width; Q.hop = env->hop;
         Q.env_rows = env->env_rows; Q.t_base = env->t_base; Q.tick0 = env->tick0;
         Q.in_lag = env->in_lag; Q.lag_stride = env->lag_stride; Q.lag_state = env->lag_state;
+        Q.lag_par = env->lag_par; Q.lag_taps = env->lag_taps;
         if (bands) return fail(HG_ERR_UNSUPPORTED, "envelope followers and per-band outputs cannot be combined");
         if (env->in_lag) return fma ? launch_ru<T, true, false, 2>(Q, st) : launch_ru<T, false, false, 2>(Q, st);
         return fma ? launch_ru<T, true, false, 1>(Q, st) : launch_ru<T, false, false, 1>(Q, st);

@@ -93,7 +93,7 @@ public:
     void process(const T* in, T* out_sum, size_t L, const std::vector<hg_fb_event>& events, int mode = HG_MODE_EXACT, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process_events(fb, in, out_sum, L, events.data(), events.size(), mode, cuda_stream));
     }
-    // follower_mode(HG_ENV_REPLICA) before the first process_env: no ring, ~2x faster, parameters must stay fixed
+    // follower_mode(HG_ENV_REPLICA) before the first process_env: no ring, ~2x faster; every tick must then go through process_env
     void follower_mode(int mode) { hg_check(hg_fb_set_follower_mode(fb, mode)); }
     void process_env(const T* in, T* out_sum, T* env, size_t L, int width = SR / 20, int hop = 64, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process_env(fb, in, out_sum, env, L, width, hop, cuda_stream));

@@ -108,11 +108,12 @@ typedef struct {
 hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t L, const hg_fb_event* events,
                                size_t n_events, int mode, void* cuda_stream);
 /* How the followers obtain y[t-width].  HG_ENV_RING (default): a ring of the last `width` squares per filter
- * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter); follows
- * parameter changes.  HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same
- * input and regenerates y[t-width] bit for bit (no ring, twice the arithmetic, ~1.7x faster on B200); the
- * coefficients, boost and mix must then stay fixed once the followers run (HG_ERR_UNSUPPORTED otherwise).
- * Call before the first hg_fb_process_env. */
+ * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter).
+ * HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same input and regenerates
+ * y[t-width] bit for bit (no ring, twice the arithmetic, ~2x faster on B200).  Parameter changes reach the
+ * replicas `width` ticks after the filters (the library keeps the pending sets and splits blocks at the
+ * hand-over ticks); the one restriction is that every tick must then be rendered through hg_fb_process_env
+ * (plain hg_fb_process is refused while replica followers run).  Call before the first hg_fb_process_env. */
 enum { HG_ENV_RING = 1, HG_ENV_REPLICA = 2 };
 hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode);
 hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_env, size_t L, int width,
