@@ -7,6 +7,8 @@
 #include "../include/huygens/latchbank.h"
 #include "../include/huygens/slidebank.h"
 #include "../include/huygens/stickbank.h"
+#include "../include/huygens/modbank.h"
+#include "../include/huygens/mixer.h"
 #include "../include/huygens/offline.h"
 
 using namespace soundmath;
@@ -26,6 +28,10 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 8; i++) radii.push_back(std::complex<double>(0.99 - 0.01 * i, 0.002 * i));
         Slidebank<double, 8> slide(2, radii);
         Stickbank<double, 8> smooth(1, -0.9);
+        Modbank<double, 8> mod;                          // tests/harmbank.cpp: mixdown(demodulators(synthesis(), ...))
+        Mixer<double, 8> mixer;
+        Oscbank<double, 8>::ArrayCT amps(8);
+        for (int i = 0; i < 8; i++) amps(i) = std::complex<double>((i + 1) / 8.0, 0.0);
         for (int i = 0; i < 8; i++) osc.freqmod(i, 110.0 * (i + 1));
         osc.freqmod(99, 1.0);       // ignored, oscbank.h:51
         osc.open();
@@ -47,8 +53,9 @@ int main(int argc, char** argv) {
             const auto* sm = smooth(slide(ph));
             std::complex<double> ssum = 0;
             for (int i = 0; i < 8; i++) ssum += (*sm)(i);
-            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum,
-                        ssum.real(), ssum.imag());
+            const double weighted = mixer(mod(&amps, ph));      // Mixer(Modbank(amps, osc())), src/modbank.h:41-45, src/mixer.h:32-35
+            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", m.real(), m.imag(), first, again, y, yd, gsum,
+                        ssum.real(), ssum.imag(), weighted);
             osc.tick(); rms.tick(); rms2.tick(); F.tick(); slide.tick(); smooth.tick();
         }
         // block entry points of the drop-in Filterbank: fused envelope followers (replica mode) and a parameter

@@ -77,6 +77,8 @@ def test_dropin_headers_compile_standalone_and_instantiate(tmp_path):
 #include "huygens/slidebank.h"
 #include "huygens/stickbank.h"
 #include "huygens/offline.h"
+#include "huygens/modbank.h"
+#include "huygens/mixer.h"
 namespace soundmath {
 template class Filterbank<float>;   template class Filterbank<double>;
 template class FFilterbank<float, 8, 2>;  template class FFilterbank<double, 96, 2>;
@@ -85,6 +87,8 @@ template class RMSbank<float, 8>;   template class RMSbank<double, 96>;
 template class Latchbank<float, 8>; template class Latchbank<double, 96>;
 template class Slidebank<float, 8>; template class Slidebank<double, 96>;
 template class Stickbank<float, 8>; template class Stickbank<double, 96>;
+template class Modbank<float, 8>;   template class Modbank<double, 96>;
+template class Mixer<float, 8>;     template class Mixer<double, 96>;
 }
 int main() { return 0; }
 """)

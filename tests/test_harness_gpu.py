@@ -92,7 +92,7 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
     lines = r.stdout.strip().splitlines()
     extra = {ln.split()[1]: float(ln.split()[2]) for ln in lines if ln.startswith("#")}
     got = np.array([[float(v) for v in line.split()] for line in lines if not line.startswith("#")])
-    assert got.shape == (ticks, 9)
+    assert got.shape == (ticks, 10)
     # the block entry points of the drop-in header: fused followers (replica mode) and a parameter schedule
     NB, L, width, hop = 16, 1200, 96, 32
 
@@ -129,6 +129,8 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
     assert np.array_equal(got[:, 2], first[0]) and np.array_equal(got[:, 3], again[0])
     gated = oracle.Latchbank(8, 0.9, 0.2, width=16).process(zre, zim)[0]
     assert np.allclose(got[:, 6], gated.sum(axis=0), rtol=0, atol=1e-13)
+    weighted = (ph.real * ((np.arange(8) + 1) / 8.0)).sum(axis=1)
+    assert np.allclose(got[:, 9], weighted, rtol=0, atol=1e-13)
     radii = np.array([complex(0.99 - 0.01 * i, 0.002 * i) for i in range(8)])
     smoothed = oracle.Stickbank(8, 1, -0.9).process(oracle.Slidebank(8, 2, radii).process(ph.T))
     assert np.allclose(got[:, 7] + 1j * got[:, 8], smoothed.sum(axis=0), rtol=0, atol=1e-13)
