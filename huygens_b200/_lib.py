@@ -36,6 +36,7 @@ SYMBOLS = [
     ("hg_fb_process_env", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_fb_set_follower_mode", _i, [_vp, _i]),
     ("hg_fb_process_events", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
+    ("hg_fb_process_tv", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     ("hg_fb_get_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_set_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_last_launch", _i, [_vp, _pi, _pi, _pi, _pi]),

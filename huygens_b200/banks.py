@@ -187,6 +187,17 @@ class Filterbank(_Handle):
         L.check(L.lib().hg_fb_process_events(self._h, _ptr(x), _ptr(out), x.shape[-1], C.cast(evs, C.c_void_p), len(events), _MODE[mode], None))
         return out
 
+    def process_tv(self, x, rows, hop=1):
+        """Block render with a parameter table: rows [n_rows][7][N] = b0 b1 b2 a1 a2 boost mix, row r replacing the
+        bank's parameters before block tick r*hop (hg_fb_process_tv; hop = 1 is audio-rate modulation)."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        rows = np.ascontiguousarray(rows, dtype=self.dtype)
+        if rows.ndim != 3 or rows.shape[1:] != (7, self.N):
+            raise ValueError("rows must be [n_rows][7][N]")
+        out = np.empty_like(x)
+        L.check(L.lib().hg_fb_process_tv(self._h, _ptr(x), _ptr(out), x.shape[-1], _ptr(rows), rows.shape[0], int(hop), None))
+        return out
+
     def process_bands(self, x, mode="exact"):
         """Per-band outputs only (no sum)."""
         x = np.ascontiguousarray(x, dtype=self.dtype)

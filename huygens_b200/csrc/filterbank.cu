@@ -129,6 +129,30 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                (A::muladd(P.s_g, r.g[f], r.cg[f]) == r.g[f]);
     }
     T x1 = P.xh[2 * s], x2 = P.xh[2 * s + 1];
+    // time-varying parameters: ticks left until the next row takes over, and that row's index
+    const bool tv = P.tv_rows != nullptr;
+    // the setters of the caller loop, all filters at once: coefficients(), boost(), mix() (filterbank.h:73-110)
+    auto tv_load = [&](long rowidx) {
+        const T* row = P.tv_rows + (size_t)rowidx * 7 * N;
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            const int n = n_base + f * NT + tid;
+            if (n < N) {
+                r.b0[f] = row[0 * (size_t)N + n]; r.b1[f] = row[1 * (size_t)N + n]; r.b2[f] = row[2 * (size_t)N + n];
+                r.a1[f] = row[3 * (size_t)N + n]; r.a2[f] = row[4 * (size_t)N + n];
+                r.cp[f] = A::mul(P.c_p, row[5 * (size_t)N + n]);
+                r.cg[f] = A::mul(P.c_g, row[6 * (size_t)N + n]);
+            }
+        }
+    };
+    long tv_row = 0, tv_left = -1;
+    if (tv) {
+        tv_row = P.tv_t0 / P.tv_hop;
+        const long into = P.tv_t0 - tv_row * P.tv_hop;          // ticks of that row already rendered by earlier launches
+        if (into > 0) { tv_load(tv_row); tv_row++; tv_left = P.tv_hop - into; }
+        else tv_left = 0;                                       // a row starts at this launch's first tick
+        conv = false;                                           // targets move: keep the smoothers on the per-sample path
+    }
 
     const T* inp = P.in + (size_t)s * P.in_stride;
     const long nchunks = (L + K1_XT - 1) / K1_XT;
@@ -203,6 +227,14 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                 }
             } else {
                 for (; tt < tn; tt++) {
+                    if (tv) {
+                        if (tv_left == 0) {
+                            tv_load(tv_row);
+                            tv_row++;
+                            tv_left = P.tv_hop;
+                        }
+                        tv_left--;
+                    }
                     const T x0 = xc[t0 + tt];
                     T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
                     x2 = x1; x1 = x0;
@@ -215,7 +247,7 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                         }
                     }
                 }
-                conv = true;
+                conv = !tv;
 #pragma unroll
                 for (int f = 0; f < F; f++)
                     conv = conv && (A::muladd(P.s_p, r.p[f], r.cp[f]) == r.p[f]) &&
@@ -294,7 +326,7 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
         *groups_out = 0;
         return;
     }
-    if (!fb->cur_dist && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
+    if (!fb->cur_dist && !fb->cur_tv && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
         fb->ws_level = level;
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
@@ -302,13 +334,13 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     }
     // throughput regime: the RU/S kernel (reported as F = -2); the lane kernel below stays for the
     // per-band nonlinearity and as a forced alternative (HG_FB_FORCE_F > 0)
-    if (!fb->cur_dist && (fb->force_F == 0 || fb->force_F == -2)) {
+    if (!fb->cur_dist && !fb->cur_tv && (fb->force_F == 0 || fb->force_F == -2)) {
         *F_out = -2;
         *groups_out = 0;
         return;
     }
     if (fb->force_F > 0) F = fb->force_F;
-    else if (fb->force_F < 0 && fb->cur_dist) F = 1;
+    else if (fb->force_F < 0 && (fb->cur_dist || fb->cur_tv)) F = 1;
     else if (lanes >= smsp_threads * 8 * 2) F = 8;
     else if (lanes >= smsp_threads * 4) F = 4;
     else if (lanes >= smsp_threads * 2) F = 2;
@@ -395,6 +427,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         hg_status rc;
         const bool fma = fb->arith == HG_ARITH_FMA;
         P.sm_slot = fb->d_sm_slot;
+        P.tv_rows = (const T*)fb->cur_tv; P.tv_hop = fb->cur_tv_hop; P.tv_t0 = (long)t0;
         if (F == 0) {
             if (fb->ws_level > 0) HG_CUDA(cudaMemsetAsync(fb->d_sm_slot, 0, 1024 * sizeof(int), st));
             rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);

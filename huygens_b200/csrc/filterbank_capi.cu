@@ -108,6 +108,7 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_lag_par) cudaFree(fb->d_lag_par);
     if (fb->d_xhist) cudaFree(fb->d_xhist);
     fb->xcat.release();
+    fb->tv_stage.release();
     delete fb;
     return HG_OK;
 }
@@ -340,6 +341,37 @@ hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t 
         }
     }
     fb->last_launches = launches;
+    return HG_OK;
+}
+
+hg_status hg_fb_process_tv(hg_fb* fb, const void* in, void* out_sum, size_t L, const void* rows, size_t n_rows, int hop,
+                           void* cuda_stream) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process_tv: null handle");
+    if (L == 0) return HG_OK;
+    if (!in || !out_sum || !rows) return hg::fail(HG_ERR_INVALID, "hg_fb_process_tv: null in/out_sum/rows");
+    if (hop < 1) return hg::fail(HG_ERR_INVALID, "hg_fb_process_tv: hop must be >= 1");
+    if (n_rows * (size_t)hop < L) return hg::fail(HG_ERR_INVALID, "hg_fb_process_tv: %zu rows of %d ticks do not cover %zu ticks", n_rows, hop, L);
+    HG_CUDA(cudaSetDevice(fb->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t es = hg::dtype_size(fb->dtype), N = fb->N, row_bytes = 7 * N * es;
+    const size_t used = (L + hop - 1) / hop;                  // rows that take effect inside this block
+    const void* d_rows = rows;
+    if (!hg::is_device_ptr(rows)) {
+        HG_TRY(fb->tv_stage.reserve(used * row_bytes));
+        HG_CUDA(cudaMemcpyAsync(fb->tv_stage.p, rows, used * row_bytes, cudaMemcpyHostToDevice, st));
+        d_rows = fb->tv_stage.p;
+    }
+    fb->cur_tv = d_rows;
+    fb->cur_tv_hop = hop;
+    hg_status rc = hg_fb_process(fb, in, out_sum, nullptr, L, HG_MODE_EXACT, HG_DIST_NONE, cuda_stream);
+    fb->cur_tv = nullptr;
+    HG_TRY(rc);
+    // the bank ends the block with the last row's parameters: device copy and host shadow follow
+    const char* last = (const char*)d_rows + (used - 1) * row_bytes;
+    HG_CUDA(cudaMemcpyAsync(fb->d_par, last, row_bytes, cudaMemcpyDeviceToDevice, st));
+    HG_CUDA(cudaMemcpyAsync(fb->h_par, last, row_bytes, cudaMemcpyDeviceToHost, st));
+    HG_CUDA(cudaStreamSynchronize(st));
+    fb->dirty = true;                                         // re-derive the tap structure at the next plain block
     return HG_OK;
 }
 

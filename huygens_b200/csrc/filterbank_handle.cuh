@@ -23,6 +23,8 @@ struct hg_fb {
     void* d_xh = nullptr;
     int xh_cur = 0;
     int cur_dist = 0;            // distortion of the block being processed
+    const void* cur_tv = nullptr;   // device rows of the block's parameter table (hg_fb_process_tv), else null
+    int cur_tv_hop = 0;
     hg::DevBuf in_stage, out_stage, bands_stage, partial, scan_a, scan_b;
     int force_F = 0;      // HG_FB_FORCE_F: 1,2,4,8 = filters per thread of the lane kernel; -1 = warp-specialised kernel
     int force_chunks = 0;
@@ -48,6 +50,7 @@ struct hg_fb {
     struct LagPending { long long tick; int taps; std::vector<unsigned char> par; };
     std::deque<LagPending> lag_pending;   // parameter sets on their way to the replicas: active from global tick `tick`
     hg::DevBuf xcat;             // replica followers: [S][width + 4 + L] history + block
+    hg::DevBuf tv_stage;         // hg_fb_process_tv: device copy of a host parameter table
     int* d_sm_slot = nullptr;        // per-SM CTA arrival counters (role rotation of co-resident ws CTAs)
     hg::DevBuf env_stage;            // residency level chosen for the warp-specialised kernel (1 << level CTAs per SM)
 };
@@ -71,6 +74,11 @@ template <typename T> struct FbK1Params {
     int dist;      // HG_DIST_*: per-band nonlinearity before the sum (lane kernel only)
     int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
     int* sm_slot;  // [>= SM count] zeroed before a launch with several CTAs per SM: arrival order of the CTAs on each SM
+    // time-varying parameters (lane kernel only): row r = [b0 b1 b2 a1 a2 pin gin][N] replaces the bank's
+    // parameters before block tick r * tv_hop (setter calls between two ticks of the caller loop)
+    const T* tv_rows;
+    int tv_hop;
+    long tv_t0;    // block tick of this launch's first sample
 };
 
 template <typename T>

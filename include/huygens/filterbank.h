@@ -93,6 +93,11 @@ public:
     void process(const T* in, T* out_sum, size_t L, const std::vector<hg_fb_event>& events, int mode = HG_MODE_EXACT, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process_events(fb, in, out_sum, L, events.data(), events.size(), mode, cuda_stream));
     }
+    // new: a block whose parameters change every `hop` ticks (hop = 1: audio-rate modulation); rows[(r * 7 + k) * N + n],
+    // k = b0 b1 b2 a1 a2 boost mix, row r taking effect before block tick r * hop
+    void process_tv(const T* in, T* out_sum, size_t L, const T* rows, size_t n_rows, int hop = 1, void* cuda_stream = nullptr) {
+        hg_check(hg_fb_process_tv(fb, in, out_sum, L, rows, n_rows, hop, cuda_stream));
+    }
     // follower_mode(HG_ENV_REPLICA) before the first process_env: no ring, ~2x faster; every tick must then go through process_env
     void follower_mode(int mode) { hg_check(hg_fb_set_follower_mode(fb, mode)); }
     void process_env(const T* in, T* out_sum, T* env, size_t L, int width = SR / 20, int hop = 64, void* cuda_stream = nullptr) {

@@ -107,6 +107,13 @@ typedef struct {
 } hg_fb_event;
 hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t L, const hg_fb_event* events,
                                size_t n_events, int mode, void* cuda_stream);
+/* new: a block whose parameters change every `hop` ticks (hop = 1: audio-rate modulation).  Row r of `rows`
+ * [n_rows][7][n_filters] = b0 b1 b2 a1 a2 boost mix replaces the bank's parameters before block tick r*hop —
+ * coefficients(n, {b0,b1,b2}, {a1,a2}), boost(values), mix(values) for every filter between two ticks of the
+ * caller loop (filterbank.h:73-110; src/subtractive.h:215-230).  One kernel, lanes reload their row at the hop
+ * boundaries; boost and mix keep their per-sample smoothing.  n_rows * hop >= L; the bank keeps the last row. */
+hg_status hg_fb_process_tv(hg_fb* fb, const void* in, void* out_sum, size_t L, const void* rows, size_t n_rows, int hop,
+                           void* cuda_stream);
 /* How the followers obtain y[t-width].  HG_ENV_RING (default): a ring of the last `width` squares per filter
  * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter).
  * HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same input and regenerates
