@@ -24,6 +24,7 @@ namespace hg {
 // ---------------------------------------------------------------------------------------------
 constexpr int K1_TILE = 32;
 constexpr int K1_XT = 1024;
+constexpr int K1_TVS = 16;     // ticks per staging step of the time-varying parameter rows
 
 template <typename T> struct Vec4 { T v[4]; };
 
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);          // [2][XT]
     T* red = xs + 2 * K1_XT;                          // [2][TILE][RS]
+    T* tvs = red + 2 * K1_TILE * RS;                  // [K1_TVS + 1][7][NT * F]: staged parameter rows (time-varying, hop < K1_TVS)
 
     const int tid = threadIdx.x;
     const int grp = blockIdx.x, s = blockIdx.y;
@@ -225,6 +227,72 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                         }
                     }
                 }
+            } else if (tv && P.tv_hop < K1_TVS) {
+                // fast parameter modulation: the rows that take effect in the next K1_TVS ticks are copied to shared
+                // memory lane by lane (coalesced, all loads in flight at once); lanes then pick their row from
+                // there at each boundary instead of waiting for seven dependent global loads per tick
+                for (int s0 = 0; s0 < tn; s0 += K1_TVS) {
+                    const int sn = min(K1_TVS, tn - s0);
+                    const int nrows = tv_left < sn ? 1 + (int)((sn - 1 - tv_left) / P.tv_hop) : 0;
+                    // every thread fetches the values of its own filters (7 * F per row): independent loads, all in
+                    // flight together, and nobody else reads them back — no barrier needed
+                    // (loads of four rows are issued before any of them is stored: an in-order warp would otherwise
+                    // wait for each load at the store that follows it)
+                    for (int r0 = 0; r0 < nrows; r0 += 4) {
+                        T tmp[4][7 * F];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const T* src = P.tv_rows + (size_t)(tv_row + r0 + u) * 7 * N;
+#pragma unroll
+                            for (int k = 0; k < 7; k++)
+#pragma unroll
+                                for (int f = 0; f < F; f++) {
+                                    const int n = n_base + f * NT + tid;
+                                    tmp[u][k * F + f] = (r0 + u < nrows && n < N) ? src[(size_t)k * N + n] : (T)0;
+                                }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            T* dst = tvs + (size_t)(r0 + u) * 7 * NT * F;
+                            if (r0 + u < nrows) {
+#pragma unroll
+                                for (int k = 0; k < 7; k++)
+#pragma unroll
+                                    for (int f = 0; f < F; f++) dst[k * NT * F + f * NT + tid] = tmp[u][k * F + f];
+                            }
+                        }
+                    }
+                    int lr = 0;
+                    for (tt = s0; tt < s0 + sn; tt++) {
+                        if (tv_left == 0) {
+                            const T* row = tvs + (size_t)lr * 7 * NT * F;
+#pragma unroll
+                            for (int f = 0; f < F; f++) {
+                                const int j = f * NT + tid;
+                                r.b0[f] = row[0 * NT * F + j]; r.b1[f] = row[1 * NT * F + j]; r.b2[f] = row[2 * NT * F + j];
+                                r.a1[f] = row[3 * NT * F + j]; r.a2[f] = row[4 * NT * F + j];
+                                r.cp[f] = A::mul(P.c_p, row[5 * NT * F + j]);
+                                r.cg[f] = A::mul(P.c_g, row[6 * NT * F + j]);
+                            }
+                            lr++;
+                            tv_row++;
+                            tv_left = P.tv_hop;
+                        }
+                        tv_left--;
+                        const T x0 = xc[t0 + tt];
+                        T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
+                        x2 = x1; x1 = x0;
+                        rb[tt * RS + tid] = acc;
+                        if (BANDS) {
+#pragma unroll
+                            for (int f = 0; f < F; f++) {
+                                const int n = n_base + f * NT + tid;
+                                if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
+                            }
+                        }
+                    }
+                }
+                conv = false;
             } else {
                 for (; tt < tn; tt++) {
                     if (tv) {
@@ -289,7 +357,8 @@ __global__ void __launch_bounds__(256) fb_reduce_partials(const T* __restrict__ 
 template <typename T, bool FMA, int F, int NT, bool BANDS>
 static hg_status launch_k1(const FbK1Params<T>& P, int groups, cudaStream_t st) {
     constexpr int NW = NT / 32;
-    const size_t smem = sizeof(T) * (2 * K1_XT + 2 * K1_TILE * (NT + NW));
+    size_t smem = sizeof(T) * (2 * K1_XT + 2 * K1_TILE * (NT + NW));
+    if (P.tv_rows && P.tv_hop < K1_TVS) smem += sizeof(T) * (size_t)(K1_TVS + 1) * 7 * NT * F;
     auto kern = fb_exact_kernel<T, FMA, F, NT, BANDS>;
     if (smem > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(groups, P.S), NT, smem, st>>>(P);
@@ -339,7 +408,8 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
         *groups_out = 0;
         return;
     }
-    if (fb->force_F > 0) F = fb->force_F;
+    if (fb->cur_tv) F = 1;                                   // time-varying rows: more CTAs, small staging buffers
+    else if (fb->force_F > 0) F = fb->force_F;
     else if (fb->force_F < 0 && (fb->cur_dist || fb->cur_tv)) F = 1;
     else if (lanes >= smsp_threads * 8 * 2) F = 8;
     else if (lanes >= smsp_threads * 4) F = 4;
