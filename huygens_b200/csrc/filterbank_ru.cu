@@ -10,9 +10,12 @@
 //     S warps   lane = sample: out[t] = sum over their RU warps (ascending) and the 32 lanes (ascending)
 //               of fma(y, g, .); own the mix gains g (replayed per sample while they still move) and
 //               stream per-band rows; S warp 0 also feeds the input ring by TMA bulk copies
-// One CTA = W RU warps + 2 S warps of one stream; full/empty mbarriers per RU warp, no __syncthreads in
-// the steady state.  7.5 (taps {g,0,-g}) to 10.5 (general taps) RU instructions + ~3 S instructions
-// per filter-sample against 11 algorithmic issue slots.
+// One CTA = W RU warps + ceil(W/2) S warps of one stream; full/empty mbarriers per RU warp, no __syncthreads
+// in the steady state, where an RU warp runs whole input chunks with nothing but the two hand-over barriers
+// per tile around the unrolled recurrence.  7.5 (taps {g,0,-g}) to 10.5 (general taps) RU instructions + ~3 S
+// instructions per filter-sample against 11 algorithmic issue slots (12.8 issued in total, ncu).
+// ENV = 1 / 2 fuses one RMSbank envelope follower per band behind the filters: ring of y^2 in HBM, or a
+// lagged replica of every filter that regenerates y[t-width] bit for bit (see FbRuParams).
 #include "hg_common.cuh"
 #include "filterbank_handle.cuh"
 
