@@ -12,6 +12,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_n1_reference.js
 for w in c1 c3 c3_8192 c3_16384 c4; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-scan > $O/bench_$w.json 2>/dev/null; done
 python bench.py --workload c4 --env --steps 5 --warmup 3 --no-cpu-baseline --no-scan > $O/bench_c4_env_replica.json 2>/dev/null
 python bench.py --workload c4 --env --followers ring --steps 5 --warmup 3 --no-cpu-baseline --no-scan > $O/bench_c4_env_ring.json 2>/dev/null
+python bench.py --workload c5 --steps 3 --warmup 3 > $O/bench_c5.json 2>/dev/null
 python tools/bench_banks.py --seconds 10 --chain > $O/bench_banks.json 2>/dev/null
 python tools/bench_banks.py --seconds 2 --channels 65536 > $O/bench_banks_65536ch.json 2>/dev/null
 # launch list of the headline command (per-launch times are cold-cache and serialised: compare shares, not absolutes)
