@@ -397,6 +397,8 @@ hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void*
 
 hg_status hg_fb_set_state(hg_fb* fb, const void* y1, const void* y2, const void* p, const void* g, const void* xhist) {
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: null handle");
+    if (fb->env_mode == HG_ENV_REPLICA && fb->d_rms_sum)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: replica followers are running (their lagged copies would no longer match the filters)");
     HG_CUDA(cudaSetDevice(fb->device));
     HG_CUDA(cudaDeviceSynchronize());
     const size_t es = hg::dtype_size(fb->dtype), SN = (size_t)fb->S * fb->N * es;
