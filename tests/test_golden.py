@@ -151,3 +151,27 @@ def test_cuda_reproduces_golden_stickbank():
     g = np.load(os.path.join(GOLD, "stickbank_f64.npz"))
     for order, rad in g["cases"]:
         assert _same_c(_run_stick(hb.Stickbank, g, int(order), float(rad)), g[f"out_{int(order)}_{float(rad)}"])
+
+
+def test_golden_vectors_regenerate_identically(oracle_lib):
+    """The committed fixtures are what tests/golden/make_golden.py produces from oracle/_ref today (skipped where
+    the reference build is not available, e.g. on the GPU box without /root/reference and without a prebuilt _ref)."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    cases = {"filterbank_dyn_f64.npz": lambda: mg.filterbank_case(np.float64, False),
+             "filterbank_fixed_f32.npz": lambda: mg.filterbank_case(np.float32, True),
+             "oscbank_f32.npz": lambda: mg.oscbank_case(np.float32),
+             "rmsbank_f64.npz": lambda: mg.rmsbank_case(np.float64),
+             "latchbank_f32.npz": lambda: mg.latchbank_case(np.float32),
+             "slidebank_f64.npz": lambda: mg.slidebank_case(np.float64),
+             "stickbank_f64.npz": mg.stickbank_case}
+    for name, make in cases.items():
+        want, got = np.load(os.path.join(GOLD, name)), make()
+        assert set(want.files) == set(got.keys()), name
+        for k in want.files:
+            a, b = np.asarray(want[k]), np.asarray(got[k])
+            assert a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes(), (name, k)
