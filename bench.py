@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-scan", action="store_true", help="skip the scan-mode side measurement")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's filters are split over the GPUs (BASELINE configs[2]) instead of N filters per GPU")
     ap.add_argument("--followers", default="replica", choices=["ring", "replica"], help="with --env: how y[t-width] is obtained (HBM ring, or lagged replica filters)")
+    ap.add_argument("--sum", default="ordered", choices=["ordered", "tree"], help="mixdown: ordered = the reference's index order and rounding (bit-identical, default); tree = per-CTA partial sums (tolerance mode)")
     ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
 
@@ -327,7 +328,7 @@ def workload_config(w, args, world):
             "filters_per_gpu": w["N"], "filters_total": w["N"] * (1 if w.get("streams", 1) > 1 else world),
             "streams_total": w.get("streams", 1) * (world if w.get("streams", 1) > 1 else 1), "samples": int(w["seconds"] * SR),
             "partition": ("streams" if w.get("streams", 1) > 1 else "filters") if world > 1 else "none", "mode": args.mode, "arith": args.arith,
-            "l2": "flushed between steps (256 MiB write)"}
+            "sum": args.sum, "l2": "flushed between steps (256 MiB write)"}
 
 
 def main():
@@ -359,7 +360,7 @@ def main():
     dtype, tdtype = (np.float64, torch.float64) if w.get("dtype") == "f64" else (np.float32, torch.float32)
     L = int(w["seconds"] * SR)
     N = w["N"]
-    fb = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local)
+    fb = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local, sum_mode=args.sum)
     S = w.get("streams", 1)
     x_host = torch.from_numpy(synth_input(w, L, dtype)).pin_memory()
     out_host = torch.empty(x_host.shape, dtype=tdtype).pin_memory()

@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhuygens_cuda.so")
+LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(_HERE, "lib", "libhuygens_cuda.so")   # HG_LIB_PATH: experiment builds
 _LIB = None
 
 HG_OK, HG_ERR_INVALID, HG_ERR_UNSUPPORTED, HG_ERR_CUDA, HG_ERR_NOMEM = 0, 1, 2, 3, 4
@@ -17,6 +17,7 @@ HG_ARITH_STRICT, HG_ARITH_FMA = 0, 1
 HG_MODE_AUTO, HG_MODE_EXACT, HG_MODE_SCAN = 0, 1, 2
 HG_FB_FIXED = 1
 HG_DIST_NONE, HG_DIST_SOFTCLIP = 0, 1
+HG_SUM_TREE, HG_SUM_ORDERED = 0, 1
 
 # every symbol include/huygens_cuda.h declares: (name, restype, argtypes)
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -40,6 +41,9 @@ SYMBOLS = [
     ("hg_fb_get_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_set_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("hg_fb_last_launch", _i, [_vp, _pi, _pi, _pi, _pi]),
+    ("hg_fb_set_sum_mode", _i, [_vp, _i]),
+    ("hg_fb_check", _i, [_vp]),
+    ("hg_fb_debug_profile", _i, [_vp, _vp, _i]),
     ("hg_osc_create", _i, [C.POINTER(_vp), _i, _i, _i, _i]),
     ("hg_osc_destroy", _i, [_vp]),
     ("hg_osc_freqmod", _i, [_vp, _i, _d]),

@@ -73,11 +73,22 @@ class Filterbank(_Handle):
     _destroy = "hg_fb_destroy"
 
     def __init__(self, order, N=1, k_p=0.1, k_g=1.0, dtype=np.float64, arith="strict", streams=1,
-                 fixed=False, device=0):
+                 fixed=False, device=0, sum_mode="ordered"):
         super().__init__(dtype, arith)
         self.order, self.N, self.streams, self.device = order, N, streams, device
         L.check(L.lib().hg_fb_create(C.byref(self._h), self.hg_dtype, self.arith, order, N, streams,
                                      k_p, k_g, L.HG_FB_FIXED if fixed else 0, device))
+        if sum_mode != "ordered":
+            self.set_sum_mode(sum_mode)
+
+    def set_sum_mode(self, mode):
+        """"ordered" (default): the mixdown is accumulated in filter-index order like the reference loop
+        (src/filterbank.h:130) — bit-identical sums; "tree": per-CTA partial sums added in a fixed tree order."""
+        L.check(L.lib().hg_fb_set_sum_mode(self._h, {"ordered": L.HG_SUM_ORDERED, "tree": L.HG_SUM_TREE}[mode]))
+
+    def check(self):
+        """Synchronous health check of the ordered mixdown (raises if its watchdog fired)."""
+        L.check(L.lib().hg_fb_check(self._h))
 
     # -- reference setters ------------------------------------------------------------------
     def coefficients(self, n, forward, back):
@@ -108,9 +119,10 @@ class Filterbank(_Handle):
         L.check(L.lib().hg_fb_open(self._h))
 
     # -- block entry point --------------------------------------------------------------------
-    def process(self, x, out=None, bands=False, mode="auto", distortion=0):
+    def process(self, x, out=None, bands=False, mode="exact", distortion=0):
         """for t: out[t] = bank(x[t]); bank.tick().  x: [L] or [streams][L].
-        Returns out (and bands [streams][N][L] when bands=True)."""
+        Returns out (and bands [streams][N][L] when bands=True).  mode "exact" (default) is bit-identical to the
+        reference loop for any block split; "scan" / "auto" may use the tolerance-bounded time-parallel scan."""
         if _is_torch(x):
             import torch
             assert x.is_cuda and x.dtype == self._torch_dtype() and x.is_contiguous()

@@ -52,23 +52,11 @@ template <typename T, int F> struct Lane {
     T y1[F], y2[F], p[F], g[F], cp[F], cg[F];
 };
 
-// tests/filterbank.cpp:158-171 softclip(sample, width = 0.125), evaluated in double like the
-// reference's `double softclip(double)` and rounded to T.  Device atan is within 2 ulp of the
-// correctly rounded value (CUDA math API), so this path is tolerance-bounded, not bit-exact.
-template <typename T> __device__ __forceinline__ T softclip_dev(T v) {
-    const double PI_REF = 3.14159265359, width = 0.125;       // src/includes.h:30
-    const double sample = (double)v;
-    if (fabs(sample) < width) return v;
-    const double sign = (0.0 < sample) - (sample < 0.0);
-    const double gap = sample - sign * width;
-    return (T)(sign * width + (1 - width) * 2.0 / PI_REF * atan(PI_REF * gap / (2 * (1 - width))));
-}
-
-// one sample for the F filters of this thread; returns sum_f y_f * g_f (or sum_f softclip(y_f * g_f))
+// one sample for the F filters of this thread.  The mixdown terms go to v[] (and the gains to gm[] in fma mode,
+// where the sum warp fuses y*g + acc): v = fl(y*g), or distortion(fl(y*g)) (:133-139); fma without distortion: v = y
 template <typename T, bool FMA, int F, bool SMOOTH, bool BANDS>
-__device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T s_g, T (&yb)[F], int dist = 0) {
+__device__ __forceinline__ void k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T s_g, T (&yb)[F], T (&v)[F], T (&gm)[F], int dist) {
     typedef Ar<T, FMA> A;
-    T acc = (T)0;
 #pragma unroll
     for (int f = 0; f < F; f++) {
         if (SMOOTH) {                                    // filterbank.h:172-173
@@ -84,27 +72,102 @@ __device__ __forceinline__ T k1_sample(Lane<T, F>& r, T x0, T x1, T x2, T s_p, T
         r.y2[f] = r.y1[f];
         r.y1[f] = y;
         if (BANDS) yb[f] = y;
-        if (dist) acc = A::add(acc, softclip_dev<T>(A::mul(y, r.g[f])));   // :133-139  sum_n distortion(y_n g_n)
-        else acc = A::acc(y, r.g[f], acc);               // :130  row . gains_out
+        if (dist) v[f] = softclip_dev<T>(A::mul(y, r.g[f]));
+        else if (FMA) { v[f] = y; gm[f] = r.g[f]; }
+        else v[f] = A::mul(y, r.g[f]);
     }
-    return acc;
 }
 
+// CTA = NT compute threads (thread = F filters) + one sum warp.  The compute threads leave the mixdown terms of a
+// 32-sample tile in shared memory, vt[t][j] with j = filter index within the CTA; the sum warp (lane = sample) adds
+// them in index order onto the running row of the chain (chain.cuh) while the compute threads render the next tile.
 template <typename T, bool FMA, int F, int NT, bool BANDS>
-__global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
+__global__ void __launch_bounds__(NT + 32) fb_exact_kernel(FbK1Params<T> P) {
     typedef Ar<T, FMA> A;
-    constexpr int NW = NT / 32;
-    constexpr int RS = NT + NW;          // row stride == NW (mod 32): STS and reduce both conflict-free
+    constexpr int NF = NT * F;
+    constexpr int RS = NF + 1;           // row stride == 1 (mod 32): the per-sample STS of all threads and the sum warp's column walk are conflict-free
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);          // [2][XT]
-    T* red = xs + 2 * K1_XT;                          // [2][TILE][RS]
-    T* tvs = red + 2 * K1_TILE * RS;                  // [K1_TVS + 1][7][NT * F]: staged parameter rows (time-varying, hop < K1_TVS)
+    T* vt = xs + 2 * K1_XT;                           // [2][TILE][RS]  mixdown terms (fma: y)
+    T* gt = vt + 2 * K1_TILE * RS;                    // [2][TILE][RS]  fma: gains
+    T* tvs = gt + (FMA ? 2 * K1_TILE * RS : 0);       // [K1_TVS + 1][7][NT * F]: staged parameter rows (time-varying, hop < K1_TVS)
 
     const int tid = threadIdx.x;
-    const int grp = blockIdx.x, s = blockIdx.y;
+    const int G = gridDim.x;
+    const unsigned ticket = chain::take_ticket(P.chain);
+    const int grp = (int)(ticket % (unsigned)G), s = (int)(ticket / (unsigned)G);
     const int N = P.N;
     const long L = P.L;
-    const int n_base = grp * NT * F;
+    const int n_base = grp * NF;
+    const long nchunks = (L + K1_XT - 1) / K1_XT;
+    const int dist = P.dist;
+
+    if (tid >= NT) {
+        // ---------------- sum warp ----------------
+        const int lane = tid - NT;
+        const chain::Params& C = P.chain;
+        const bool summing = P.out != nullptr || C.outbox != nullptr;
+        const bool ordered = C.ordered != 0;
+        const bool head = !ordered || grp == 0, tail = !ordered || grp == G - 1;
+        constexpr int WPS = chain::Words<T>::WPS;
+        chain::Port<T, 1> pin, pout;
+        if (ordered && summing) {
+            if (!head) pin.open(C.ring + (((size_t)s * G + grp) << C.ring_log2) * WPS, C.credit + (size_t)s * G + grp, C);
+            else if (C.inbox) pin.open(C.inbox + ((size_t)s << C.ring_log2) * WPS, C.inbox_credit + s, C);
+            if (!tail) pout.open(C.ring + (((size_t)s * G + grp + 1) << C.ring_log2) * WPS, C.credit + (size_t)s * G + grp + 1, C);
+            else if (C.outbox) pout.open(C.outbox + ((size_t)s << C.ring_log2) * WPS, C.outbox_credit + s, C);
+        }
+        T* out_row = nullptr;
+        if (P.out && tail && !pout.on())
+            out_row = (ordered || P.direct) ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
+        const T* carry = (ordered && head && !pin.on() && P.carry_in) ? P.carry_in + (size_t)s * P.carry_stride : nullptr;
+        const int cols = min(NF, N - n_base);                 // filters of this CTA
+        typename chain::Port<T, 1>::Raw raw;
+        bool issued = false;
+        if (pin.on() && lane < L) { pin.issue(C, lane, raw); issued = true; }
+        long tile_idx = 0;
+        for (long c = 0; c < nchunks; c++) {
+            __syncthreads_and(1);
+            const int cnt = (int)min((long)K1_XT, L - c * K1_XT);
+            for (int t0 = 0; t0 < cnt; t0 += K1_TILE, tile_idx++) {
+                __syncthreads_and(1);                         // the compute threads have finished this tile
+                const int tn = min(K1_TILE, cnt - t0);
+                const long tg = c * K1_XT + t0;
+                if (!summing) continue;
+                T acc = (T)0;
+                if (pin.on()) {
+                    T a1v[1] = {(T)0};
+                    if (tg + lane < L) pin.recv(C, tg + lane, a1v, raw, issued);
+                    acc = a1v[0];
+                    issued = false;
+                    if (tg + K1_TILE + lane < L) { pin.issue(C, tg + K1_TILE + lane, raw); issued = true; }
+                } else if (carry) {
+                    if (lane < tn) acc = carry[tg + lane];
+                }
+                const T* vr = vt + (tile_idx & 1) * (K1_TILE * RS) + lane * RS;
+                const T* gr = gt + (tile_idx & 1) * (K1_TILE * RS) + lane * RS;
+                if (FMA && !dist) {
+#pragma unroll 8
+                    for (int j = 0; j < cols; j++) acc = A::muladd(vr[j], gr[j], acc);        // :130
+                } else {
+#pragma unroll 8
+                    for (int j = 0; j < cols; j++) acc = A::add(vr[j], acc);                   // :130 / :137
+                }
+                if (pout.on()) {
+                    pout.reserve(C, tg + K1_TILE);
+                    T a1v[1] = {acc};
+                    pout.send(C, tg + lane, a1v);
+                } else if (out_row) {
+                    if (lane < tn) out_row[tg + lane] = acc;
+                }
+                if (pin.on()) {
+                    __syncwarp();
+                    if (lane == 0) pin.release(C, tg + K1_TILE);
+                }
+            }
+        }
+        return;
+    }
 
     Lane<T, F> r;
     const size_t SN = (size_t)P.S * N;
@@ -157,7 +220,6 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
     }
 
     const T* inp = P.in + (size_t)s * P.in_stride;
-    const long nchunks = (L + K1_XT - 1) / K1_XT;
     auto stage = [&](long c) {
         const long base = c * K1_XT;
         const int cnt = (int)min((long)K1_XT, L - base);
@@ -167,10 +229,21 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
     };
     if (nchunks > 0) stage(0);
 
-    T* out_row = P.direct ? (P.out + (size_t)s * P.out_stride)
-                          : (P.out + ((size_t)grp * P.S + s) * (size_t)L);
     long tile_idx = 0;
     int all_conv = 0;
+    T ybs[F], vv[F], gg[F];
+    // one sample: render, leave the mixdown terms in the tile, stream the band rows
+    auto emit = [&](T* vrow, T* grow, long tglob) {
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            vrow[f * NT + tid] = vv[f];
+            if (FMA) grow[f * NT + tid] = gg[f];
+            if (BANDS) {
+                const int n = n_base + f * NT + tid;
+                if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tglob] = ybs[f];
+            }
+        }
+    };
     for (long c = 0; c < nchunks; c++) {
         if (c + 1 < nchunks) {
             stage(c + 1);
@@ -183,49 +256,16 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
         const T* xc = xs + (c & 1) * K1_XT;
         for (int t0 = 0; t0 < cnt; t0 += K1_TILE, tile_idx++) {
             const int tn = min(K1_TILE, cnt - t0);
-            T* rb = red + (tile_idx & 1) * (K1_TILE * RS);
+            T* vb = vt + (tile_idx & 1) * (K1_TILE * RS);
+            T* gb = gt + (tile_idx & 1) * (K1_TILE * RS);
             const long tg = c * K1_XT + t0;          // time index of the tile start in this block
             int tt = 0;
-            T yb[F][4];
-            T ybs[F];
             if (all_conv) {
-                for (; tt + 4 <= tn; tt += 4) {
-                    T xv[4];
-                    lds4<T>(xc + t0 + tt, xv);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        T acc = k1_sample<T, FMA, F, false, BANDS>(r, xv[k], x1, x2, P.s_p, P.s_g, ybs, P.dist);
-                        x2 = x1; x1 = xv[k];
-                        rb[(tt + k) * RS + tid] = acc;
-                        if (BANDS) {
-#pragma unroll
-                            for (int f = 0; f < F; f++) yb[f][k] = ybs[f];
-                        }
-                    }
-                    if (BANDS) {
-#pragma unroll
-                        for (int f = 0; f < F; f++) {
-                            const int n = n_base + f * NT + tid;
-                            if (n < N) {
-                                T* bp = P.bands + ((size_t)s * N + n) * P.bands_stride + tg + tt;
-                                if (P.bands_vec) stg4<T>(bp, yb[f]);
-                                else { bp[0] = yb[f][0]; bp[1] = yb[f][1]; bp[2] = yb[f][2]; bp[3] = yb[f][3]; }
-                            }
-                        }
-                    }
-                }
                 for (; tt < tn; tt++) {
                     const T x0 = xc[t0 + tt];
-                    T acc = k1_sample<T, FMA, F, false, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
+                    k1_sample<T, FMA, F, false, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, vv, gg, dist);
                     x2 = x1; x1 = x0;
-                    rb[tt * RS + tid] = acc;
-                    if (BANDS) {
-#pragma unroll
-                        for (int f = 0; f < F; f++) {
-                            const int n = n_base + f * NT + tid;
-                            if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
-                        }
-                    }
+                    emit(vb + tt * RS, gb + tt * RS, tg + tt);
                 }
             } else if (tv && P.tv_hop < K1_TVS) {
                 // fast parameter modulation: the rows that take effect in the next K1_TVS ticks are copied to shared
@@ -280,16 +320,9 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                         }
                         tv_left--;
                         const T x0 = xc[t0 + tt];
-                        T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
+                        k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, vv, gg, dist);
                         x2 = x1; x1 = x0;
-                        rb[tt * RS + tid] = acc;
-                        if (BANDS) {
-#pragma unroll
-                            for (int f = 0; f < F; f++) {
-                                const int n = n_base + f * NT + tid;
-                                if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
-                            }
-                        }
+                        emit(vb + tt * RS, gb + tt * RS, tg + tt);
                     }
                 }
                 conv = false;
@@ -304,16 +337,9 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                         tv_left--;
                     }
                     const T x0 = xc[t0 + tt];
-                    T acc = k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, P.dist);
+                    k1_sample<T, FMA, F, true, BANDS>(r, x0, x1, x2, P.s_p, P.s_g, ybs, vv, gg, dist);
                     x2 = x1; x1 = x0;
-                    rb[tt * RS + tid] = acc;
-                    if (BANDS) {
-#pragma unroll
-                        for (int f = 0; f < F; f++) {
-                            const int n = n_base + f * NT + tid;
-                            if (n < N) P.bands[((size_t)s * N + n) * P.bands_stride + tg + tt] = ybs[f];
-                        }
-                    }
+                    emit(vb + tt * RS, gb + tt * RS, tg + tt);
                 }
                 conv = !tv;
 #pragma unroll
@@ -321,10 +347,8 @@ __global__ void __launch_bounds__(NT) fb_exact_kernel(FbK1Params<T> P) {
                     conv = conv && (A::muladd(P.s_p, r.p[f], r.cp[f]) == r.p[f]) &&
                            (A::muladd(P.s_g, r.g[f], r.cg[f]) == r.g[f]);
             }
+            // hand the tile to the sum warp (it adds tile k while tile k+1 is rendered into the other buffer)
             all_conv = __syncthreads_and(conv);
-            // transposed reduction of the tile: warp w owns samples [w*SPW, (w+1)*SPW); NW lanes
-            // per sample, each summing 32 of the NT per-thread partials, then a shuffle tree.
-            if (P.out) cta_tile_reduce<T, NT>(rb, tn, out_row + tg);
         }
     }
     // state write-back
@@ -356,12 +380,11 @@ __global__ void __launch_bounds__(256) fb_reduce_partials(const T* __restrict__ 
 
 template <typename T, bool FMA, int F, int NT, bool BANDS>
 static hg_status launch_k1(const FbK1Params<T>& P, int groups, cudaStream_t st) {
-    constexpr int NW = NT / 32;
-    size_t smem = sizeof(T) * (2 * K1_XT + 2 * K1_TILE * (NT + NW));
+    size_t smem = sizeof(T) * (2 * K1_XT + (FMA ? 4 : 2) * K1_TILE * (size_t)(NT * F + 1));
     if (P.tv_rows && P.tv_hop < K1_TVS) smem += sizeof(T) * (size_t)(K1_TVS + 1) * 7 * NT * F;
     auto kern = fb_exact_kernel<T, FMA, F, NT, BANDS>;
     if (smem > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(groups, P.S), NT, smem, st>>>(P);
+    kern<<<dim3(groups, P.S), NT + 32, smem, st>>>(P);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
@@ -371,53 +394,59 @@ static hg_status launch_k1_F(int F, const FbK1Params<T>& P, int groups, cudaStre
     switch (F) {
         case 1: return launch_k1<T, FMA, 1, NT, BANDS>(P, groups, st);
         case 2: return launch_k1<T, FMA, 2, NT, BANDS>(P, groups, st);
-        case 4: return launch_k1<T, FMA, 4, NT, BANDS>(P, groups, st);
-        case 8: return launch_k1<T, FMA, 8, NT, BANDS>(P, groups, st);
     }
-    return fail(HG_ERR_INVALID, "bad F %d", F);
+    return fail(HG_ERR_INVALID, "lane kernel: %d filters per thread is not built (1, 2)", F);
 }
 
-// choose filters-per-thread so that the grid covers the SMs; more filters per thread amortise the
-// per-sample reduction overhead, fewer expose more lanes.
+// Kernel choice.  F_out = 0: warp-specialised kernel (latency-bound regime: every CTA of 32 filters resident at
+// once, 1, 2 or 4 per SM; fp64: 1 or 2); -2: RU/S kernel (throughput regime, fused followers); 1, 2: lane kernel
+// with that many filters per thread (time-varying parameter tables, or forced).
 static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
-    const long lanes = (long)fb->N * fb->S;
-    const long smsp_threads = (long)fb->sm_count * 4 * 32;   // one warp per scheduler
-    int F = 1;
-    // latency-bound regime: every CTA of 32 filters resident at once, 1, 2 or 4 per SM (fp64: 1 or 2)
-    // -> the warp-specialised kernel, reported as F = 0
     const long ws_ctas = (long)((fb->N + 31) / 32) * fb->S;
     const int max_level = fb->dtype == HG_F32 ? 2 : 1;
     int level = 0;
     while (level < max_level && ws_ctas > ((long)fb->sm_count << level)) level++;
     const bool ws_fits = ws_ctas <= ((long)fb->sm_count << level);
-    if (fb->cur_env) {                   // fused envelope followers live in the RU/S kernel
-        *F_out = -2;
-        *groups_out = 0;
-        return;
-    }
-    if (!fb->cur_dist && !fb->cur_tv && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
+    *groups_out = 0;
+    if (fb->cur_env) { *F_out = -2; return; }              // fused envelope followers live in the RU/S kernel
+    if (!fb->cur_tv && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
         fb->ws_level = level;
         *F_out = 0;
         *groups_out = (fb->N + 31) / 32;
         return;
     }
-    // throughput regime: the RU/S kernel (reported as F = -2); the lane kernel below stays for the
-    // per-band nonlinearity and as a forced alternative (HG_FB_FORCE_F > 0)
-    if (!fb->cur_dist && !fb->cur_tv && (fb->force_F == 0 || fb->force_F == -2)) {
-        *F_out = -2;
-        *groups_out = 0;
-        return;
-    }
-    if (fb->cur_tv) F = 1;                                   // time-varying rows: more CTAs, small staging buffers
-    else if (fb->force_F > 0) F = fb->force_F;
-    else if (fb->force_F < 0 && (fb->cur_dist || fb->cur_tv)) F = 1;
-    else if (lanes >= smsp_threads * 8 * 2) F = 8;
-    else if (lanes >= smsp_threads * 4) F = 4;
-    else if (lanes >= smsp_threads * 2) F = 2;
-    // a single stream cannot use more filters/thread than fills one group sensibly
-    while (F > 1 && fb->N < K1_NT * F / 2) F >>= 1;
+    if (!fb->cur_tv && (fb->force_F == 0 || fb->force_F == -2)) { *F_out = -2; return; }
+    int F = 1;
+    if (!fb->cur_tv && fb->force_F == 2 && fb->dtype == HG_F32) F = 2;
     *F_out = F;
     *groups_out = (fb->N + K1_NT * F - 1) / (K1_NT * F);
+}
+
+// rings, credits, ticket counter and watchdog flag of the ordered mixdown for `links` chain links
+static hg_status chain_reserve(hg_fb* fb, size_t links, cudaStream_t st) {
+    const size_t wps = hg::dtype_size(fb->dtype) / 4;
+    int lg = 11;
+    while (lg > 8 && ((links << lg) * wps * 8) > ((size_t)256 << 20)) lg--;
+    if (!fb->d_ticket) {
+        HG_CUDA(cudaMalloc((void**)&fb->d_ticket, sizeof(unsigned)));
+        HG_CUDA(cudaMemsetAsync(fb->d_ticket, 0, sizeof(unsigned), st));
+        HG_CUDA(cudaMalloc((void**)&fb->d_chain_error, sizeof(int)));
+        HG_CUDA(cudaMemsetAsync(fb->d_chain_error, 0, sizeof(int), st));
+    }
+    if (links > fb->chain_links || lg != fb->chain_ring_log2) {
+        // a new geometry: fresh, zeroed rings (tag 0 is never valid), so no stale tag of another ring size can match
+        if (fb->d_chain_ring) HG_CUDA(cudaFree(fb->d_chain_ring));
+        if (fb->d_chain_credit) HG_CUDA(cudaFree(fb->d_chain_credit));
+        fb->d_chain_ring = nullptr; fb->d_chain_credit = nullptr; fb->chain_links = 0;
+        const size_t words = (links << lg) * wps;
+        cudaError_t ce;
+        if ((ce = cudaMalloc(&fb->d_chain_ring, words * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&fb->d_chain_credit, links * 8)) != cudaSuccess)
+            return fail(HG_ERR_NOMEM, "ordered mixdown: %zu links of %d samples: %s", links, 1 << lg, cudaGetErrorString(ce));
+        HG_CUDA(cudaMemsetAsync(fb->d_chain_ring, 0, words * 8, st));
+        HG_CUDA(cudaMemsetAsync(fb->d_chain_credit, 0, links * 8, st));
+        fb->chain_links = links; fb->chain_ring_log2 = lg; fb->chain_ring_words = words;
+    }
+    return HG_OK;
 }
 
 template <typename T>
@@ -431,11 +460,13 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
     }
     fb->last_F = F;
     fb->last_ctas = (F == -2 ? ru_cps : groups) * fb->S;
-    // ws kernel: thread-block clusters reduce the per-CTA partial sums in distributed shared memory
-    int cs = 1;
-    if (F == 0) cs = fb->force_cluster >= 1 ? fb->force_cluster : fb_ws_cluster_size<T>(groups, fb->S, fb->ws_level);
-    if (cs < 1 || groups % cs) cs = 1;
-    const int rows = groups / cs;            // partial-sum rows that reach HBM
+    // ordered mixdown (default): the running row travels through the CTAs, the chain's tail writes out[t] — one
+    // row, no scratch.  Tree mode: one partial row per CTA, added up by fb_reduce_partials.
+    const bool peer = fb->cur_peer.inbox || fb->cur_peer.outbox;
+    const bool summing = d_out != nullptr || fb->cur_peer.outbox != nullptr;
+    const bool ordered = fb->sum_mode != 0 || peer || fb->cur_carry_in;
+    const int rows = ordered ? 1 : groups;   // partial-sum rows that reach HBM
+    HG_TRY(chain_reserve(fb, ordered && summing ? (size_t)groups * fb->S : 1, st));
     // segment the block so the partial-sum scratch stays bounded
     size_t seg = L;
     if (rows > 1 && d_out) {
@@ -490,6 +521,19 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.bands_vec = (vec_ok && (t0 % 4 == 0)) ? 1 : 0;
         P.taps = fb->taps;
         P.dist = fb->cur_dist;
+        P.chain = fb->cur_peer;
+        P.chain.ring = (unsigned long long*)fb->d_chain_ring;
+        P.chain.credit = fb->d_chain_credit;
+        P.chain.vbase = fb->chain_vbase;
+        P.chain.ticket = fb->d_ticket;
+        P.chain.ticket_base = fb->ticket_base;
+        P.chain.error = fb->d_chain_error;
+        P.chain.ring_log2 = fb->chain_ring_log2;
+        P.chain.ordered = ordered ? 1 : 0;
+        P.prof = nullptr;
+        if (fb->d_prof && fb->last_ctas <= 4096) { HG_CUDA(cudaMemsetAsync(fb->d_prof, 0, 4096 * 8 * sizeof(long long), st)); P.prof = fb->d_prof; }
+        P.carry_in = fb->cur_carry_in ? (const T*)fb->cur_carry_in + t0 : nullptr;
+        P.carry_stride = (long)L;
         P.N = fb->N;
         P.S = fb->S;
         P.L = (long)len;
@@ -500,7 +544,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.tv_rows = (const T*)fb->cur_tv; P.tv_hop = fb->cur_tv_hop; P.tv_t0 = (long)t0;
         if (F == 0) {
             if (fb->ws_level > 0) HG_CUDA(cudaMemsetAsync(fb->d_sm_slot, 0, 1024 * sizeof(int), st));
-            rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, cs, fb->ws_level, P, groups, st);
+            rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, fb->ws_level, P, groups, st);
         }
         else if (F == -2) {
             FbEnvArgs<T> E;
@@ -519,6 +563,9 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);
         HG_TRY(rc);
         fb->last_launches++;
+        // the next launch's virtual positions start on a fresh lap of the largest ring; its CTAs take tickets after these
+        fb->chain_vbase += (((unsigned long long)len + 2047ull) & ~2047ull) + 2048ull;
+        fb->ticket_base += (unsigned)fb->last_ctas;
         if (!P.direct && d_out) {
             dim3 grid((unsigned)((len + 255) / 256), fb->S);
             fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, rows, fb->S, (long)len, (long)L);

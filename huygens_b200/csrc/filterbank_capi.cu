@@ -72,8 +72,8 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     if (e) fb->force_F = atoi(e);
     e = getenv("HG_FB_FORCE_CHUNKS");
     if (e) fb->force_chunks = atoi(e);
-    e = getenv("HG_FB_CLUSTER");
-    if (e) fb->force_cluster = atoi(e);
+    e = getenv("HG_FB_PROF");
+    if (e && atoi(e)) cudaMalloc((void**)&fb->d_prof, 4096 * 8 * sizeof(long long));
     cudaError_t ce;
     if ((ce = cudaMallocHost(&fb->h_par, 7 * N * es)) != cudaSuccess ||
         (ce = cudaMalloc(&fb->d_par, 7 * N * es)) != cudaSuccess ||
@@ -100,6 +100,11 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_state) cudaFree(fb->d_state);
     if (fb->d_xh) cudaFree(fb->d_xh);
     if (fb->d_sm_slot) cudaFree(fb->d_sm_slot);
+    if (fb->d_chain_ring) cudaFree(fb->d_chain_ring);
+    if (fb->d_chain_credit) cudaFree(fb->d_chain_credit);
+    if (fb->d_ticket) cudaFree(fb->d_ticket);
+    if (fb->d_chain_error) cudaFree(fb->d_chain_error);
+    if (fb->d_prof) cudaFree(fb->d_prof);
     fb->in_stage.release(); fb->out_stage.release(); fb->bands_stage.release(); fb->partial.release();
     fb->scan_a.release(); fb->scan_b.release(); fb->env_stage.release();
     if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);
@@ -250,7 +255,40 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     bool need_sync = !in_dev;
     if (out_sum && !out_dev) { HG_CUDA(cudaMemcpyAsync(out_sum, d_out, S * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
     if (out_bands && !bands_dev) { HG_CUDA(cudaMemcpyAsync(out_bands, d_bands, S * N * L * es, cudaMemcpyDeviceToHost, st)); need_sync = true; }
-    if (need_sync) HG_CUDA(cudaStreamSynchronize(st));
+    if (need_sync) {
+        HG_CUDA(cudaStreamSynchronize(st));
+        HG_TRY(hg_fb_check(fb));
+    }
+    return HG_OK;
+}
+
+hg_status hg_fb_check(hg_fb* fb) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_check: null handle");
+    if (!fb->d_chain_error) return HG_OK;
+    HG_CUDA(cudaSetDevice(fb->device));
+    int flag = 0;
+    HG_CUDA(cudaMemcpy(&flag, fb->d_chain_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(fb->d_chain_error, 0, sizeof(int));
+        return hg::fail(HG_ERR_CUDA, "ordered mixdown: a CTA gave up waiting for the running bank-sum row of its predecessor (watchdog); the block's sum is invalid");
+    }
+    return HG_OK;
+}
+
+hg_status hg_fb_debug_profile(hg_fb* fb, long long* out, int n_ctas) {
+    if (!fb || !out) return hg::fail(HG_ERR_INVALID, "hg_fb_debug_profile: null argument");
+    if (!fb->d_prof) return hg::fail(HG_ERR_INVALID, "hg_fb_debug_profile: create the handle with HG_FB_PROF=1 in the environment");
+    if (n_ctas > 4096) n_ctas = 4096;
+    HG_CUDA(cudaSetDevice(fb->device));
+    HG_CUDA(cudaDeviceSynchronize());
+    HG_CUDA(cudaMemcpy(out, fb->d_prof, (size_t)n_ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return HG_OK;
+}
+
+hg_status hg_fb_set_sum_mode(hg_fb* fb, int mode) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_sum_mode: null handle");
+    if (mode != HG_SUM_ORDERED && mode != HG_SUM_TREE) return hg::fail(HG_ERR_INVALID, "hg_fb_set_sum_mode: bad mode %d", mode);
+    fb->sum_mode = mode == HG_SUM_ORDERED ? 1 : 0;
     return HG_OK;
 }
 
@@ -387,6 +425,7 @@ hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void*
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_get_state: null handle");
     HG_CUDA(cudaSetDevice(fb->device));
     HG_CUDA(cudaDeviceSynchronize());
+    HG_TRY(hg_fb_check(fb));
     const size_t es = hg::dtype_size(fb->dtype), SN = (size_t)fb->S * fb->N * es;
     void* dst[4] = {y1, y2, p, g};
     for (int k = 0; k < 4; k++)

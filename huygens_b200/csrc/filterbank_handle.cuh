@@ -4,6 +4,15 @@
 #include <deque>
 #include <vector>
 #include "hg_common.cuh"
+#include "chain.cuh"
+
+// Role cycle counters of the exact kernels (hg_fb_debug_profile): compiled in only with -DHG_FB_PROFILE, so the
+// production kernels carry no timing code.
+#ifdef HG_FB_PROFILE
+#define HG_PROF_ON(P) ((P).prof != nullptr)
+#else
+#define HG_PROF_ON(P) false
+#endif
 
 constexpr int K1_NT = 128;   // threads per CTA of the exact kernel (one warp per SM sub-partition)
 
@@ -28,7 +37,21 @@ struct hg_fb {
     hg::DevBuf in_stage, out_stage, bands_stage, partial, scan_a, scan_b;
     int force_F = 0;      // HG_FB_FORCE_F: 1,2,4,8 = filters per thread of the lane kernel; -1 = warp-specialised kernel
     int force_chunks = 0;
-    int force_cluster = -1;   // HG_FB_CLUSTER: cluster size of the ws kernel (1 disables), -1 = automatic
+    // order-faithful mixdown (chain.cuh): link rings and credits, the virtual sample position, the CTA ticket counter
+    int sum_mode = 1;                      // HG_SUM_ORDERED (1, default) or HG_SUM_TREE (0)
+    void* d_chain_ring = nullptr;          // [links][ring samples] LL words
+    size_t chain_ring_words = 0;
+    int chain_ring_log2 = 0;
+    unsigned long long* d_chain_credit = nullptr;
+    size_t chain_links = 0;
+    unsigned long long chain_vbase = 0;    // multiple of the ring size, grows with every launch
+    unsigned* d_ticket = nullptr;          // [1] CTA arrival counter, never reset: launches subtract `ticket_base`
+    unsigned ticket_base = 0;
+    int* d_chain_error = nullptr;          // [1] watchdog flag
+    long long* d_prof = nullptr;           // debug (HG_FB_PROF=1 at create): [ctas][8] role cycle counters of the last launch
+    // the chain's ends for the block being processed (set by the sharded entry points, else null)
+    const void* cur_carry_in = nullptr;    // [S][L] running row to start from (null: zero)
+    hg::chain::Params cur_peer = {};       // inbox / outbox of a multi-GPU chain (ring, credit fields unused)
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
     int ws_level = 0;
@@ -73,6 +96,10 @@ template <typename T> struct FbK1Params {
     int bands_vec;
     int dist;      // HG_DIST_*: per-band nonlinearity before the sum (lane kernel only)
     int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
+    chain::Params chain;      // how the bank sum travels from CTA to CTA (chain.cuh)
+    long long* prof;          // debug (HG_FB_PROF): per-CTA cycle counters of the S / R roles, or null
+    const T* carry_in;        // [S] rows (stride carry_stride): the running sum the chain's head starts from; null = 0
+    long carry_stride;
     int* sm_slot;  // [>= SM count] zeroed before a launch with several CTAs per SM: arrival order of the CTAs on each SM
     // time-varying parameters (lane kernel only): row r = [b0 b1 b2 a1 a2 pin gin][N] replaces the bank's
     // parameters before block tick r * tv_hop (setter calls between two ticks of the caller loop)
@@ -84,9 +111,7 @@ template <typename T> struct FbK1Params {
 template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
 template <typename T>
-hg_status fb_launch_exact_ws(bool fma, bool bands, int cluster, int level, const FbK1Params<T>& P, int groups, cudaStream_t st);
-template <typename T>
-int fb_ws_cluster_size(int groups, int streams, int level);
+hg_status fb_launch_exact_ws(bool fma, bool bands, int level, const FbK1Params<T>& P, int groups, cudaStream_t st);
 template <typename T> struct FbEnvArgs {
     T* env; T* rms_sum; T* rms_ring;
     int width, hop;

@@ -7,10 +7,19 @@
 // shortest critical path.
 //     RU warps  lane = filter: feed-forward taps, pre-gain and the recurrence (x by LDS.128 broadcast,
 //               y out by STS.128 into a 2-deep ring of [32][TILE] tiles); own y1, y2 and p
-//     S warps   lane = sample: out[t] = sum over their RU warps (ascending) and the 32 lanes (ascending)
-//               of fma(y, g, .); own the mix gains g (replayed per sample while they still move) and
-//               stream per-band rows; S warp 0 also feeds the input ring by TMA bulk copies
-// One CTA = W RU warps + ceil(W/2) S warps of one stream; full/empty mbarriers per RU warp, no __syncthreads
+//     S warps   lane = sample: add the filters of their RU warps, in index order and with the reference's rounding
+//               (src/filterbank.h:130,137), onto the running bank-sum row: S warp i receives it from S warp i-1
+//               (shared memory), S warp 0 from the CTA of the filters before and the last S warp hands it to the
+//               next CTA (chain.cuh); the chain's tail writes out[t].  They own the mix gains g (replayed per
+//               sample while they still move) and stream per-band rows; S warp 0 also feeds the input ring by
+//               TMA bulk copies
+//     G warp    the chain's gateway: keeps the inbound packets of the next two tiles in flight and drops the running
+//               row into shared memory for S warp 0, so no S warp ever waits on an L2 round trip
+// Tile formats.  Strict arithmetic without per-band output or followers (VF): the RU warps also own the mix gains and
+// leave the mixdown TERMS v = fl(y*g) in the tile, sample-major [32 samples][32 filters]: an S warp fetches the 32
+// terms of its sample with 8 LDS.128 and its whole stage is the 32-deep FADD chain.  Otherwise the tile holds y,
+// filter-major, and the S warps own the gains (fused multiply-add, per-band rows, followers reading y back).
+// One CTA = W RU warps + ceil(W/2) S warps + the gateway, of one stream; full/empty mbarriers per RU warp, no __syncthreads
 // in the steady state, where an RU warp runs whole input chunks with nothing but the two hand-over barriers
 // per tile around the unrolled recurrence.  7.5 (taps {g,0,-g}) to 10.5 (general taps) RU instructions + ~3 S
 // instructions per filter-sample against 11 algorithmic issue slots (12.8 issued in total, ncu).
@@ -18,6 +27,7 @@
 // lagged replica of every filter that regenerates y[t-width] bit for bit (see FbRuParams).
 #include "hg_common.cuh"
 #include "filterbank_handle.cuh"
+#include "chain.cuh"
 
 namespace hg {
 
@@ -32,6 +42,7 @@ constexpr int W_MAX_ENV = 8;  // ... with fused envelope followers: fewer warps,
 constexpr int GPS = 2;        // RU warps served by one S warp: an S warp must not need more than its fair share
                               // of its scheduler's issue slots, or the RU warps starve behind it
 constexpr int NS_MAX = (W_MAX + GPS - 1) / GPS;
+constexpr int PD = 4;         // depth of the running-row hand-over between consecutive S warps
 __host__ __device__ constexpr int s_warps(int W) { return (W + GPS - 1) / GPS; }
 
 template <typename T> struct RowStride;      // RS*sizeof(T)/16 odd: conflict-free 128-bit rows
@@ -62,6 +73,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_poll(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
 template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&x)[4]);
 template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&x)[4]) {
     float4 v = *reinterpret_cast<const float4*>(p);
@@ -81,7 +102,7 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
 }
 
 // dynamic shared memory layout (W known at launch):
-//   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[2][NS][32] | barriers
+//   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[NS][PD][32] | barriers
 template <typename T> struct Layout {
     static constexpr int RS = RowStride<T>::RS;
     int W, NS, LAG;       // LAG: the replica followers add a second input ring
@@ -91,10 +112,10 @@ template <typename T> struct Layout {
     __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NB * 32 * RS; }
     __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * NS * 32 * RS; }
     __host__ __device__ size_t ps_off() const { return gs_off() + sizeof(T) * NS * GPS * 32; }
-    __host__ __device__ size_t xl_off() const { return (ps_off() + sizeof(T) * 2 * NS * 32 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xl_off() const { return (ps_off() + sizeof(T) * PD * NS * 32 + 15) & ~(size_t)15; }
     __host__ __device__ size_t yl_off() const { return xl_off() + sizeof(T) * (size_t)LAG * XB * XT; }
     __host__ __device__ size_t bar_off() const { return (yl_off() + 15) & ~(size_t)15; }
-    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB + 4); }
+    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB + 2 * PD * NS); }
 };
 
 }  // namespace ru
@@ -143,6 +164,26 @@ __device__ __forceinline__ void ru_tile(const T* __restrict__ xc, T* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; j++) yy[j] = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
         st4<T>(yrow + 4 * q, yy);
+    }
+}
+
+// VF tiles: the same recurrence, the mixdown term v = fl(y*g) stored sample-major (vcol = tile + lane, row stride VS)
+template <typename T, bool FMA, int TAPS>
+__device__ __forceinline__ void ru_tile_v(const T* __restrict__ xc, T* __restrict__ vcol, T b0, T b1, T b2, T a1, T a2, T p, T g,
+                                          T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2) {
+    using namespace ru;
+    typedef Ar<T, FMA> A;
+    constexpr int VS = RowStride<T>::RS;
+    T xq[2][4];
+    ld4<T>(xc, xq[0]);
+#pragma unroll
+    for (int q = 0; q < TILE / 4; q++) {
+        if (q + 1 < TILE / 4) ld4<T>(xc + 4 * (q + 1), xq[(q + 1) & 1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const T y = ru_sample<T, FMA, TAPS>(xq[q & 1][j], b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+            vcol[(4 * q + j) * VS] = A::mul(y, g);               // filterbank.h:130  y_n * g_n
+        }
     }
 }
 
@@ -201,11 +242,12 @@ template <typename T> struct FbRuParams {
 
 // ENV: 0 no followers; 1 followers with the ring of y^2 in HBM; 2 followers with lagged replicas
 template <typename T, bool FMA, bool BANDS, int ENV>
-__global__ void __launch_bounds__(ENV == 1 ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV)) * 32 : (ru::W_MAX + ru::NS_MAX) * 32, 1)
+__global__ void __launch_bounds__(ENV == 1 ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV) + 1) * 32 : (ru::W_MAX + ru::NS_MAX + 1) * 32, 1)
 fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
     constexpr int RS = RowStride<T>::RS;
+    constexpr bool VF = !FMA && !BANDS && ENV == 0;          // tiles hold the mixdown terms, sample-major
     const FbK1Params<T>& P = Q.k;
     const int W = Q.W;
     const int NS = s_warps(W);
@@ -222,11 +264,13 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     unsigned long long* x_empty = bars + XB;                // [XB]
     unsigned long long* y_full = bars + 2 * XB;             // [W][NB]
     unsigned long long* y_empty = bars + 2 * XB + W * NB;   // [W][NB]
-    unsigned long long* ps_full = bars + 2 * XB + 2 * W * NB;       // [2] partial sums of S warps 1.. ready
-    unsigned long long* ps_empty = ps_full + 2;                      // [2] S warp 0 has consumed them
+    unsigned long long* ps_full = bars + 2 * XB + 2 * W * NB;       // [NS][PD] running row of S warp i ready for S warp i+1
+    unsigned long long* ps_empty = ps_full + PD * NS;                // [NS][PD] ... consumed
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cta = blockIdx.x, s = blockIdx.y;
+    // chain position = arrival order (chain.cuh): CTA (s, cta) owns the filter groups [cta W, cta W + W) of stream s
+    const unsigned ticket = chain::take_ticket(P.chain);
+    const int cta = (int)(ticket % gridDim.x), s = (int)(ticket / gridDim.x);
     const int N = P.N;
     const long L = P.L;
     const int groups = (N + 31) / 32;                       // RU warps of the whole stream
@@ -241,11 +285,97 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < XB; i++) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], w_here); }
         for (int i = 0; i < W * NB; i++) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&ps_full[i], NS - 1); mbar_init(&ps_empty[i], 1); }
+        for (int i = 0; i < PD * NS; i++) { mbar_init(&ps_full[i], 1); mbar_init(&ps_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    // the chain (chain.cuh): where this CTA's running bank-sum row comes from
+    const chain::Params& C = P.chain;
+    const int G = gridDim.x;
+    const bool summing = P.out != nullptr || C.outbox != nullptr;
+    const bool ordered = C.ordered != 0;
+    const bool head = !ordered || cta == 0, tail = !ordered || cta == G - 1;
+    const bool has_in = ordered && summing && (!head || C.inbox != nullptr);
+    constexpr int WPS = chain::Words<T>::WPS;
+
+    if (warp == W + NS) {
+        // ------------------------------ G: input loader + chain gateway ------------------------------
+        // One polling loop, never blocked on either duty: an input chunk is issued (TMA bulk copy) as soon as every
+        // RU warp has released its ring slot — the RU warps of the later S warps run a few tiles behind those of
+        // the first, so whoever waits for that must not be a stage of the chain; the inbound packets of the next
+        // two tiles are kept in flight and land in shared memory as soon as their tags are complete.
+        const T* inp = P.in + (size_t)s * P.in_stride;
+        const T* inlp = ENV == 2 ? Q.in_lag + (size_t)s * Q.lag_stride : nullptr;
+        chain::Port<T, 1> pin;
+        if (has_in) {
+            if (!head) pin.open(C.ring + (((size_t)s * G + cta) << C.ring_log2) * WPS, C.credit + (size_t)s * G + cta, C);
+            else pin.open(C.inbox + ((size_t)s << C.ring_log2) * WPS, C.inbox_credit + s, C);
+        }
+        typename chain::Port<T, 1>::Raw r0, r1;
+        const int gtiles = has_in ? ntiles : 0;
+        if (gtiles > 0 && lane < L) pin.issue(C, lane, r0);
+        if (gtiles > 1 && TILE + lane < L) pin.issue(C, TILE + lane, r1);
+        unsigned long long* gfull = ps_full + (NS - 1) * PD;        // the hand-over slots of the (unused) link after the last S warp
+        unsigned long long* gempty = ps_empty + (NS - 1) * PD;
+        T* gslot = psum + (size_t)(NS - 1) * PD * 32;
+        int c = 0, gk = 0;
+        unsigned spins = 0;
+        while (c < nchunks || gk < gtiles) {
+            bool progress = false;
+            const int b = c % XB;
+            if (c < nchunks && mbar_poll(&x_empty[b], (unsigned)(((c / XB) & 1) ^ 1))) {
+                const long base = (long)c * XT;
+                const int cnt = (int)min((long)XT, L - base);
+                const T* src = inp + base;
+                const T* srcl = ENV == 2 ? inlp + base : src;
+                const unsigned bytes = (unsigned)(cnt * sizeof(T));
+                if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)srcl) & 15) == 0 && (bytes & 15) == 0) {
+                    if (lane == 0) {
+                        mbar_arrive_tx(&x_full[b], ENV == 2 ? 2 * bytes : bytes);
+                        bulk_g2s(xs + b * XT, src, bytes, &x_full[b]);
+                        if (ENV == 2) bulk_g2s(xls + b * XT, srcl, bytes, &x_full[b]);
+                    }
+                } else {
+                    for (int i = lane; i < cnt; i += 32) {
+                        xs[b * XT + i] = src[i];
+                        if (ENV == 2) xls[b * XT + i] = srcl[i];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&x_full[b]);
+                }
+                c++;
+                progress = true;
+            }
+            const int pb = gk % PD;
+            if (gk < gtiles && mbar_poll(&gempty[pb], (unsigned)(((gk / PD) & 1) ^ 1))) {
+                const long t = (long)gk * TILE + lane;
+                const bool got = !(t < L) || pin.ready(C, t, r0);
+                if (__all_sync(0xffffffffu, got)) {
+                    T v[1];
+                    memcpy(v, r0.w, sizeof(v));
+                    gslot[pb * 32 + lane] = v[0];
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&gfull[pb]);
+                        pin.release(C, (long)(gk + 1) * TILE);       // the packet is in shared memory: its ring slot is free
+                    }
+                    gk++;
+                    r0 = r1;
+                    if (gk + 1 < gtiles && (long)(gk + 1) * TILE + lane < L) pin.issue(C, (long)(gk + 1) * TILE + lane, r1);
+                    progress = true;
+                } else if (!got) {
+                    pin.issue(C, t, r0);                             // poll again (this lane's packet only)
+                }
+            }
+            if (progress) spins = 0;
+            else {
+                __nanosleep(32);          // nothing to do right now: leave the issue and shared-memory pipes to the other roles
+                if (++spins > chain::SPIN_LIMIT / 8) { *C.error = 1; break; }
+            }
+        }
+        return;
+    }
     if (warp < W) {
         // ------------------------------ RU: taps, pre-gain, recurrence ------------------------------
         if (warp >= w_here) return;
@@ -263,7 +393,11 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         T m1 = A::mul(b0, x1), m2 = A::mul(b0, x2);         // taps == 2: fl(b0 x[t-1]), fl(b0 x[t-2])
         const int taps = P.taps;
         bool conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
-        T* ybase = ytiles + (size_t)warp * NB * 32 * RS + lane * RS;
+        // VF: this warp owns the mix gain smoother too (filterbank.h:173) and writes v = fl(y*g)
+        T g = (VF && ok) ? P.state[3 * SN + si] : (T)0;
+        const T cg = VF ? A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0) : (T)0, s_g = P.s_g;
+        if (VF) conv = conv && __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);     // `conv`: both smoothers at their fixed point
+        T* ybase = ytiles + (size_t)warp * NB * 32 * RS + (VF ? lane : lane * RS);
         unsigned long long* yf = y_full + warp * NB;
         unsigned long long* ye = y_empty + warp * NB;
         int xb = 0, yb = 0, kc = 0;
@@ -315,17 +449,22 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             }
         }
         static_assert(NB == 2, "the steady-state loop toggles between two tile slots");
+        long long pf_gate = 0, pf_x = 0;
+        const long long pf_t0 = HG_PROF_ON(P) ? clock64() : 0;
         for (int k = 0; k < ntiles; k++) {
             if (ENV == 0 && conv && kc == 0 && (long)(k + TPC) * TILE <= L) {
                 // steady state: a whole input chunk of full tiles with converged smoothers.  Nothing but the two
                 // hand-over barriers per tile around the unrolled recurrence (the general path below spends ~75
                 // instructions per tile on cases that cannot occur here).
-                mbar_wait(&x_full[xb], xpar);
+                { const long long pc0 = HG_PROF_ON(P) ? clock64() : 0; mbar_wait(&x_full[xb], xpar); if (HG_PROF_ON(P)) pf_x += clock64() - pc0; }
                 const T* xcb = xs + xb * XT;
 #define HG_RU_CHUNK(TP)                                                                                          \
                 _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
+                    const long long pc0 = HG_PROF_ON(P) ? clock64() : 0;                                               \
                     mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
-                    ru_tile<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2); \
+                    if (HG_PROF_ON(P)) pf_gate += clock64() - pc0;                                                     \
+                    if (VF) ru_tile_v<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2); \
+                    else ru_tile<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2); \
                     __syncwarp();                                                                               \
                     if (lane == 0) mbar_arrive(&yf[yb]);                                                        \
                     ypar ^= (unsigned)yb;                                                                       \
@@ -402,11 +541,16 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 fused = true;
             } else if (conv && tn == TILE) {
                 // whole tile unrolled; `taps` is uniform, so pick the specialised body once per tile
-                if (taps == 2) ru_tile<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
+                if (VF) {
+                    if (taps == 2) ru_tile_v<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2);
+                    else if (taps == 1) ru_tile_v<T, FMA, 1>(xc, yrow, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2);
+                    else ru_tile_v<T, FMA, 0>(xc, yrow, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2);
+                }
+                else if (taps == 2) ru_tile<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                 else if (taps == 1) ru_tile<T, FMA, 1>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                 else ru_tile<T, FMA, 0>(xc, yrow, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2);
                 tt = TILE;
-            } else if (conv) {
+            } else if (conv && !VF) {
                 for (; tt + 4 <= tn; tt += 4) {
                     T xv[4], yy[4];
                     ld4<T>(xc + tt, xv);
@@ -417,6 +561,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             }
             for (; tt < tn; tt++) {
                 if (!conv) p = A::muladd(s_p, p, cp);                              // filterbank.h:172
+                if (VF && !conv) g = A::muladd(s_g, g, cg);                        // filterbank.h:173
                 const T x0 = xc[tt];
                 T fw = A::mul(b0, x0);
                 fw = A::muladd(b1, x1, fw);
@@ -426,10 +571,11 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 const T y = A::mulsub(fw, p, fb);
                 y2 = y1; y1 = y;
                 x2 = x1; x1 = x0;
-                yrow[tt] = y;
+                if (VF) yrow[tt * RS] = A::mul(y, g);                              // filterbank.h:130  y_n * g_n
+                else yrow[tt] = y;
             }
             if (!conv || tn != TILE) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
-            if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p);
+            if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p && (!VF || A::muladd(s_g, g, cg) == g));
             if (ENV == 2 && !fused) {
                 // replica + follower, sample by sample (stream start, smoothers still moving, ragged tile, hop < TILE)
                 const T* xlc = xls + xb * XT + kc * TILE;
@@ -528,10 +674,15 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         }
         if (ok) {
             P.state[0 * SN + si] = y1; P.state[1 * SN + si] = y2; P.state[2 * SN + si] = p;
+            if (VF) P.state[3 * SN + si] = g;
             if (ENV) Q.rms_sum[si] = rsum;
             if (ENV == 2) { Q.lag_state[0 * SN + si] = y1l; Q.lag_state[1 * SN + si] = y2l; Q.lag_state[2 * SN + si] = pl; }
         }
         if (cta == 0 && warp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+        if (HG_PROF_ON(P) && lane == 0 && (warp == 0 || warp == w_here - 1)) {
+            long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8 + (warp == 0 ? 4 : 6);
+            q[0] = pf_gate; q[1] = warp == 0 ? pf_x : clock64() - pf_t0;
+        }
     } else {
         // ------------------------------ S: mixdown, gains, input ring ------------------------------
         const int sidx = warp - W;                          // 0 .. NS-1
@@ -539,7 +690,6 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         // RU warps served by this S warp: an even split of the CTA's active RU warps
         const int per = (w_here + NS - 1) / NS;
         const int wa = min(w_here, sidx * per), wb = min(w_here, wa + per);
-        const bool feeds = sidx == 0;
         T* gt = gtiles + (size_t)sidx * 32 * RS;
         T* gs = gsmem + (size_t)sidx * GPS * 32;            // converged gains, [served RU warp][filter]
         // lane l holds g, cg of filter l of every served RU warp
@@ -549,7 +699,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         for (int i = 0; i < GPS; i++) {
             const int w = wa + i;
             const int n = (w_first + w) * 32 + lane;
-            const bool ok = w < wb && n < N;
+            const bool ok = !VF && w < wb && n < N;
             g[i] = ok ? P.state[3 * SN + (size_t)s * N + n] : (T)0;
             cg[i] = A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0);
             gconv = gconv && (A::muladd(P.s_g, g[i], cg[i]) == g[i]);
@@ -557,53 +707,73 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         }
         gconv = __all_sync(0xffffffffu, gconv);
         __syncwarp();
-        const T* inp = P.in + (size_t)s * P.in_stride;
-        const T* inlp = ENV == 2 ? Q.in_lag + (size_t)s * Q.lag_stride : nullptr;
-        T* out_row = P.out ? P.out + ((size_t)cta * P.S + s) * (size_t)L : nullptr;     // one partial row per CTA
-        int xb = 0, yb = 0, kc = 0;
-        unsigned xpar = 0, ypar = 0;
-        int next_chunk = 0;
+        // the running bank-sum row: in from the S warp before (S warp 0: from the gateway), out to the next S warp /
+        // CTA / device
+        const bool first = sidx == 0, last = sidx == NS - 1;
+        const bool smem_in = !first || has_in;
+        const int in_link = first ? NS - 1 : sidx - 1;
+        chain::Port<T, 1> pout;
+        if (ordered && summing && last) {
+            if (!tail) pout.open(C.ring + (((size_t)s * G + cta + 1) << C.ring_log2) * WPS, C.credit + (size_t)s * G + cta + 1, C);
+            else if (C.outbox) pout.open(C.outbox + ((size_t)s << C.ring_log2) * WPS, C.outbox_credit + s, C);
+        }
+        T* out_row = nullptr;
+        if (P.out && last && tail && !pout.on())
+            out_row = ordered ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)cta * P.S + s) * (size_t)L);   // tree mode: one partial row per CTA
+        const T* carry = (ordered && first && head && !has_in && P.carry_in) ? P.carry_in + (size_t)s * P.carry_stride : nullptr;
+        const int dist = P.dist;
+        int yb = 0;
+        unsigned ypar = 0;
+        long long pf_in = 0, pf_y = 0, pf_mix = 0, pf_out = 0;
         for (int k = 0; k < ntiles; k++) {
-            if (feeds) {
-                // keep the input ring full: chunk c may be issued once its slot was released
-                while (next_chunk < nchunks && next_chunk < (k / TPC) + XB) {
-                    const int c = next_chunk, b = c % XB;
-                    mbar_wait(&x_empty[b], (unsigned)(((c / XB) & 1) ^ 1));
-                    const long base = (long)c * XT;
-                    const int cnt = (int)min((long)XT, L - base);
-                    const T* src = inp + base;
-                    const T* srcl = ENV == 2 ? inlp + base : src;
-                    const unsigned bytes = (unsigned)(cnt * sizeof(T));
-                    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)srcl) & 15) == 0 && (bytes & 15) == 0) {
-                        if (lane == 0) {
-                            mbar_arrive_tx(&x_full[b], ENV == 2 ? 2 * bytes : bytes);
-                            bulk_g2s(xs + b * XT, src, bytes, &x_full[b]);
-                            if (ENV == 2) bulk_g2s(xls + b * XT, srcl, bytes, &x_full[b]);
-                        }
-                    } else {
-                        for (int i = lane; i < cnt; i += 32) {
-                            xs[b * XT + i] = src[i];
-                            if (ENV == 2) xls[b * XT + i] = srcl[i];
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&x_full[b]);
-                    }
-                    next_chunk++;
-                }
-            }
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
             const long tg = (long)k * TILE;
             T acc = (T)0;
             bool still = false;
+            const int pb = k % PD;
+            const unsigned ppar = (unsigned)((k / PD) & 1);
+            long long pc0 = HG_PROF_ON(P) ? clock64() : 0, pc1;
+            if (summing) {
+                if (smem_in) {
+                    // running row after the filters before this S warp's (left by S warp sidx-1, or by the gateway)
+                    mbar_wait(&ps_full[in_link * PD + pb], ppar);
+                    acc = psum[((size_t)in_link * PD + pb) * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ps_empty[in_link * PD + pb]);
+                } else if (carry) {
+                    if (lane < tn) acc = carry[tg + lane];
+                }
+            }
+            if (HG_PROF_ON(P)) { pc1 = clock64(); pf_in += pc1 - pc0; pc0 = pc1; }
 #pragma unroll 1
             for (int w = wa; w < wb; w++) {
                 const int i = w - wa;
                 mbar_wait(&y_full[w * NB + yb], ypar);
+                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_y += pc1 - pc0; pc0 = pc1; }
                 const T* yt = ytiles + ((size_t)w * NB + yb) * 32 * RS + lane;
-                // out[t] += sum_l fma(y_l[t], g_l[t], .): four interleaved partial sums over l (ascending),
-                // combined pairwise — the same fixed order whether the gains still move or not
-                T a0 = (T)0, a1s = (T)0, a2s = (T)0, a3 = (T)0;
-                if (!gconv) {
+                const int rows = min(32, N - (w_first + w) * 32);
+                // acc = fl(fl(y_l[t] * g_l[t]) + acc) (fused in fma mode), l ascending: src/filterbank.h:130 — the same
+                // function of (y, g) whether the gains still move or not
+                if (VF) {
+                    // the tile holds the terms v_l[t], sample-major: this lane's 32 terms are one 128-byte row.  Lanes
+                    // past the bank's last filter wrote +0 terms (coefficients, state and gains are zero there).
+                    const T* vr = ytiles + ((size_t)w * NB + yb) * 32 * RS + lane * RS;
+                    if (dist) {
+                        for (int l = 0; l < rows; l++) acc = A::add(acc, softclip_dev<T>(vr[l]));                                 // :137
+                    } else if (rows == 32) {
+                        constexpr int CH = sizeof(T) == 4 ? 32 : 16;      // terms fetched per batch (registers)
+#pragma unroll
+                        for (int c0 = 0; c0 < 32; c0 += CH) {
+                            T v[CH];
+#pragma unroll
+                            for (int q = 0; q < CH / 4; q++) ld4<T>(vr + c0 + 4 * q, *reinterpret_cast<T(*)[4]>(&v[4 * q]));
+#pragma unroll
+                            for (int l = 0; l < CH; l++) acc = A::add(v[l], acc);
+                        }
+                    } else {
+                        for (int l = 0; l < rows; l++) acc = A::add(vr[l], acc);
+                    }
+                } else if (!gconv) {
                     T gi = (T)0, cgi = (T)0;
 #pragma unroll
                     for (int j = 0; j < GPS; j++) if (j == i) { gi = g[j]; cgi = cg[j]; }
@@ -614,65 +784,66 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                     for (int j = 0; j < GPS; j++) if (j == i) g[j] = gi;
                     gs[i * 32 + lane] = gi;
                     __syncwarp();
-#pragma unroll
-                    for (int l = 0; l < 32; l += 4) {
-                        a0 = A::acc(yt[(l + 0) * RS], gt[(l + 0) * RS + lane], a0);                     // filterbank.h:130
-                        a1s = A::acc(yt[(l + 1) * RS], gt[(l + 1) * RS + lane], a1s);
-                        a2s = A::acc(yt[(l + 2) * RS], gt[(l + 2) * RS + lane], a2s);
-                        a3 = A::acc(yt[(l + 3) * RS], gt[(l + 3) * RS + lane], a3);
+                    if (dist) {
+                        for (int l = 0; l < rows; l++) acc = A::add(acc, softclip_dev<T>(A::mul(yt[l * RS], gt[l * RS + lane])));   // :137
+                    } else {
+#pragma unroll 8
+                        for (int l = 0; l < rows; l++) acc = A::muladd(yt[l * RS], gt[l * RS + lane], acc);
                     }
                     __syncwarp();
                 } else {
                     const T* gw = gs + i * 32;
+                    if (dist) {
+                        for (int l = 0; l < rows; l++) acc = A::add(acc, softclip_dev<T>(A::mul(yt[l * RS], gw[l])));               // :137
+                    } else if (rows == 32) {
 #pragma unroll
-                    for (int l = 0; l < 32; l += 4) {
-                        T g4[4];
-                        ld4<T>(gw + l, g4);                                  // broadcast, one LDS per 4 filters
-                        a0 = A::acc(yt[(l + 0) * RS], g4[0], a0);
-                        a1s = A::acc(yt[(l + 1) * RS], g4[1], a1s);
-                        a2s = A::acc(yt[(l + 2) * RS], g4[2], a2s);
-                        a3 = A::acc(yt[(l + 3) * RS], g4[3], a3);
+                        for (int l = 0; l < 32; l += 4) {
+                            T g4[4];
+                            ld4<T>(gw + l, g4);                                  // broadcast, one LDS per 4 filters
+                            acc = A::muladd(yt[(l + 0) * RS], g4[0], acc);
+                            acc = A::muladd(yt[(l + 1) * RS], g4[1], acc);
+                            acc = A::muladd(yt[(l + 2) * RS], g4[2], acc);
+                            acc = A::muladd(yt[(l + 3) * RS], g4[3], acc);
+                        }
+                    } else {
+                        for (int l = 0; l < rows; l++) acc = A::muladd(yt[l * RS], gw[l], acc);
                     }
                 }
-                acc += (a0 + a1s) + (a2s + a3);
                 if (BANDS) {
-                    const int rows = min(32, N - (w_first + w) * 32);
                     for (int l = 0; l < rows; l++)
                         if (lane < tn) P.bands[((size_t)s * N + (w_first + w) * 32 + l) * P.bands_stride + tg + lane] = yt[l * RS];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&y_empty[w * NB + yb]);
+                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_mix += pc1 - pc0; pc0 = pc1; }
             }
             if (!gconv) gconv = !__any_sync(0xffffffffu, still);
-            if (out_row) {
-                // combine the S warps' partial sums in fixed order through a 2-deep mbarrier hand-over:
-                // S warps 1.. publish and move on, S warp 0 adds the rows in order and writes the CTA's row
-                const int pb = k & 1;
-                const unsigned ppar = (unsigned)((k >> 1) & 1);
-                T* ps = psum + (size_t)pb * NS * 32;
-                if (sidx != 0) {
-                    mbar_wait(&ps_empty[pb], ppar ^ 1u);
-                    ps[sidx * 32 + lane] = acc;
+            if (summing) {
+                if (!last) {
+                    mbar_wait(&ps_empty[sidx * PD + pb], ppar ^ 1u);
+                    psum[((size_t)sidx * PD + pb) * 32 + lane] = acc;
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ps_full[pb]);
-                } else {
-                    mbar_wait(&ps_full[pb], ppar);
-                    T tot = acc;
-#pragma unroll
-                    for (int i = 1; i < NS; i++) tot += ps[i * 32 + lane];
-                    if (lane < tn) out_row[tg + lane] = tot;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ps_empty[pb]);
+                    if (lane == 0) mbar_arrive(&ps_full[sidx * PD + pb]);
+                } else if (pout.on()) {
+                    pout.reserve(C, tg + TILE);
+                    T a1v[1] = {acc};
+                    pout.send(C, tg + lane, a1v);
+                } else if (out_row) {
+                    if (lane < tn) out_row[tg + lane] = acc;
                 }
             }
+            if (HG_PROF_ON(P)) pf_out += clock64() - pc0;
             if (++yb == NB) { yb = 0; ypar ^= 1u; }
-            if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
         }
 #pragma unroll
         for (int i = 0; i < GPS; i++) {
             const int w = wa + i;
             const int n = (w_first + w) * 32 + lane;
-            if (w < wb && n < N) P.state[3 * SN + (size_t)s * N + n] = g[i];
+            if (!VF && w < wb && n < N) P.state[3 * SN + (size_t)s * N + n] = g[i];
+        }
+        if (HG_PROF_ON(P) && lane == 0 && sidx == (NS > 1 ? 1 : 0)) {       // a middle S warp (inbound from shared memory)
+            long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8;
+            q[0] = pf_in; q[1] = pf_y; q[2] = pf_mix; q[3] = pf_out;
         }
     }
 }
@@ -689,6 +860,8 @@ void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
     for (int per_sm = 1; per_sm <= 2; per_sm++) {
         for (int W = 4; W <= w_max; W++) {
             if ((ru::Layout<T>(W, fb->env_mode == 2 && fb->cur_env).bytes() + 1024) * per_sm > smem_sm) continue;
+            // registers: 80 per thread (launch bounds), W RU warps + their S warps + the gateway
+            if ((long)(W + ru::s_warps(W) + 1) * 32 * 80 * per_sm > 65536) continue;
             const long slots = (long)fb->sm_count * per_sm;
             const long ctas = (long)((groups + W - 1) / W) * fb->S;
             const long waves = (ctas + slots - 1) / slots;
@@ -711,7 +884,7 @@ static hg_status launch_ru(const FbRuParams<T>& Q, cudaStream_t st) {
     const size_t smem = ru::Layout<T>(Q.W, ENV == 2).bytes();
     auto kern = fb_exact_ru_kernel<T, FMA, BANDS, ENV>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W)) * 32, smem, st>>>(Q);
+    kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W) + 1) * 32, smem, st>>>(Q);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }

@@ -39,7 +39,9 @@ bool is_device_ptr(const void* p);
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policies.  STRICT never lets the compiler contract (intrinsics with explicit
 // rounding are never fused by nvcc); FMA uses the one fixed contraction pattern shared with
-// oracle/huygens_oracle.hpp.  `acc` is the order-free accumulation (mixdown), always fused.
+// oracle/huygens_oracle.hpp.  The mixdown term is `muladd(y, g, acc)` in both modes: fl(fl(y*g) + acc) strict,
+// fma(y, g, acc) fused — accumulated in filter-index order (chain.cuh).  `acc` (always fused) is only used by
+// the tolerance-mode scan.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool FMA> struct Ar;
 
@@ -76,6 +78,20 @@ template <bool FMA> struct Ar<double, FMA> {
     static __device__ __forceinline__ T div(T a, T b) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ T sqrt(T a) { return __dsqrt_rn(a); }
 };
+
+// tests/filterbank.cpp:158-171 softclip(sample, width = 0.125), evaluated in double like the
+// reference's `double softclip(double)` and rounded to T.  Device atan is within 2 ulp of the
+// correctly rounded value (CUDA math API), so this path is tolerance-bounded, not bit-exact.
+// __noinline__: one copy of the double-precision atan per kernel instead of one per unrolled call site — the hot
+// kernels' code must stay small enough for the instruction caches (the recurrence warps stream ~10 KB loops).
+template <typename T> __device__ __noinline__ T softclip_dev(T v) {
+    const double PI_REF = 3.14159265359, width = 0.125;       // src/includes.h:30
+    const double sample = (double)v;
+    if (fabs(sample) < width) return v;
+    const double sign = (0.0 < sample) - (sample < 0.0);
+    const double gap = sample - sign * width;
+    return (T)(sign * width + (1 - width) * 2.0 / PI_REF * atan(PI_REF * gap / (2 * (1 - width))));
+}
 
 // Transposed CTA reduction of one tile of per-thread partial sums.
 //   rb[t * RS + tid], RS = NT + NW  (RS == NW mod 32: the per-sample STS of all threads and the

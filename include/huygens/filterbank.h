@@ -79,7 +79,7 @@ public:
     void tick() { computed = false; }
 
     // new: block form of `out[t] = bank(in[t]); bank.tick();` — host or device pointers
-    void process(const T* in, T* out_sum, size_t L, int mode = HG_MODE_AUTO, void* cuda_stream = nullptr) {
+    void process(const T* in, T* out_sum, size_t L, int mode = HG_MODE_EXACT, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process(fb, in, out_sum, nullptr, L, mode, HG_DIST_NONE, cuda_stream));
     }
     // new: per-band outputs y_n[t], bands[n * L + t] (the reference keeps `outputs` private, :155)

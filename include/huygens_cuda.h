@@ -133,8 +133,21 @@ hg_status hg_fb_set_state(hg_fb* fb, const void* y1, const void* y2, const void*
 /* what the last hg_fb_process did: mode used, kernel launches, filters per thread, CTAs */
 hg_status hg_fb_last_launch(hg_fb* fb, int* mode_used, int* launches, int* filters_per_thread,
                             int* grid_ctas);
-/* Partial-sum device buffer helper for filter-partitioned multi-GPU runs: the caller reduces
- * out_sum across ranks (NCCL) — this library never communicates. */
+/* How operator()'s N-way mixdown is evaluated (src/filterbank.h:130, :137).
+ * HG_SUM_ORDERED (default): sum_n fl(y_n*g_n) accumulated in filter-index order in T, exactly the reference loop
+ *   (fused multiply-add in HG_ARITH_FMA): the running row travels from CTA to CTA through L2-resident rings.
+ *   out_sum is bit-identical to the reference/oracle.
+ * HG_SUM_TREE: every CTA sums its own filters and the partial rows are added in a fixed tree order — same
+ *   per-filter values, different summation order (float: ~3e-5 of peak at 4096 filters, 3e-4 at 65 536). */
+enum { HG_SUM_TREE = 0, HG_SUM_ORDERED = 1 };
+hg_status hg_fb_set_sum_mode(hg_fb* fb, int mode);
+/* Synchronous health check (copies one flag from the device): HG_ERR_CUDA if the ordered mixdown's watchdog fired
+ * during an earlier asynchronous block.  Host-pointer blocks check this before returning. */
+hg_status hg_fb_check(hg_fb* fb);
+/* Debug aid: with HG_FB_PROF=1 in the environment at hg_fb_create, the warp-specialised kernel records per-CTA cycle
+ * counters of its S and R roles (waits for the y tile, for the running row, mixdown, hand-over; R's barrier waits and
+ * total).  Copies [n_ctas][8] counters of the last launch (chain order).  Not part of the reference's surface. */
+hg_status hg_fb_debug_profile(hg_fb* fb, long long* counters, int n_ctas);
 
 /* ---- Oscbank<T,N>  (src/oscbank.h, src/multichannel.h) ------------------------------------ */
 hg_status hg_osc_create(hg_osc** out, int dtype, int arith, int n_partials, int device);   /* oscbank.h:37-47 */

@@ -49,6 +49,7 @@ def lib():
             f("hgo_fb_mix").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
             f("hgo_fb_open").argtypes = [C.c_void_p]
             f("hgo_fb_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+            f("hgo_fb_process_from").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
             f("hgo_fb_get_smoothed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             f("hgo_osc_create").restype = C.c_void_p
             f("hgo_osc_create").argtypes = [C.c_int, C.c_int]
@@ -141,11 +142,54 @@ class Filterbank(_Base):
         self._f("hgo_fb_process")(self._h, _ptr(x), _ptr(out), _ptr(bd), L, distortion)
         return (out, bd) if bands else out
 
+    def process_from(self, x, carry, distortion=0):
+        """The bank sum continued from the running row `carry` (the sum over the filters that precede this
+        bank's in a larger bank); carry = 0 gives process()."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        carry = np.ascontiguousarray(carry, dtype=self.dtype)
+        out = np.empty(len(x), self.dtype)
+        self._f("hgo_fb_process_from")(self._h, _ptr(x), _ptr(carry), _ptr(out), len(x), distortion)
+        return out
+
     def smoothed(self):
         p = np.empty(self.N, self.dtype)
         g = np.empty(self.N, self.dtype)
         self._f("hgo_fb_get_smoothed")(self._h, _ptr(p), _ptr(g))
         return p, g
+
+
+def chained_sum(banks, x, block=4096, distortion=0):
+    """Bank sum of the concatenation of `banks` (consecutive filter partitions of one bank), in the single
+    bank's index order: partition p continues the running row of partition p-1 (Filterbank.process_from).
+    One host thread per partition, pipelined over blocks of `block` samples — the same operations as one
+    oracle bank of all the filters, bit for bit (tests/test_oracle_kat.py), at len(banks) times the speed."""
+    import threading
+    x = np.ascontiguousarray(x, dtype=banks[0].dtype)
+    L = len(x)
+    nb = (L + block - 1) // block
+    rows = [np.zeros(L, banks[0].dtype)] + [np.empty(L, banks[0].dtype) for _ in banks]
+    done = [[threading.Event() for _ in range(nb)] for _ in banks]
+    errors = []
+
+    def run(p):
+        try:
+            for j in range(nb):
+                if p > 0:
+                    done[p - 1][j].wait()
+                a, b = j * block, min(L, (j + 1) * block)
+                rows[p + 1][a:b] = banks[p].process_from(x[a:b], rows[p][a:b], distortion)
+                done[p][j].set()
+        except Exception as e:          # release the threads behind us
+            errors.append(e)
+            for j in range(nb):
+                done[p][j].set()
+
+    th = [threading.Thread(target=run, args=(p,)) for p in range(len(banks))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errors:
+        raise errors[0]
+    return rows[-1]
 
 
 class Oscbank(_Base):

@@ -122,17 +122,23 @@ public:
     void open() { for (int i = 0; i < N; i++) gains_in[i] = 1; }                // :112-116
 
     // :125-131   outputs.row(origin) * gains_out, summed in index order
-    T operator()(T sample) {
+    T operator()(T sample) { return mix_from(sample, (T)0); }
+    // :133-139   sum_n distortion(y_n * g_n)
+    T operator()(T sample, T (*distortion)(T)) { return mix_from(sample, (T)0, distortion); }
+    // The same two loops with the accumulator starting from `init` instead of 0.  Test helper, not in the
+    // reference: it lets a bank be evaluated as consecutive filter partitions on several host threads (the
+    // partition [a, b) continues the running sum of [0, a)) with exactly the operations of the single loop,
+    // so full-size oracle sums take seconds instead of a minute.  init = 0 is the reference's operator().
+    T mix_from(T sample, T init) {
         if (!computed) compute(sample);
-        T acc = 0;
+        T acc = init;
         const T* row = &outputs[(size_t)origin * N];
         for (int n = 0; n < N; n++) acc = Arith<T, FMA>::muladd(row[n], gains_out[n], acc);
         return acc;
     }
-    // :133-139   sum_n distortion(y_n * g_n)
-    T operator()(T sample, T (*distortion)(T)) {
+    T mix_from(T sample, T init, T (*distortion)(T)) {
         if (!computed) compute(sample);
-        T acc = 0;
+        T acc = init;
         const T* row = &outputs[(size_t)origin * N];
         for (int n = 0; n < N; n++) acc += distortion(row[n] * gains_out[n]);
         return acc;

@@ -194,3 +194,21 @@ def test_strict_and_fma_modes_diverge_in_float(oracle_lib):
     c = make_resonator(oracle.Filterbank, 32, np.float64, mode="strict").process(x.astype(np.float64))
     d = make_resonator(oracle.Filterbank, 32, np.float64, mode="fma").process(x.astype(np.float64))
     assert rel_err(c, d) < 1e-12
+
+
+@pytest.mark.parametrize("mode", ["strict", "fma"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_chained_partitions_equal_single_bank(oracle_lib, dtype, mode):
+    """oracle.chained_sum (consecutive filter partitions, each continuing the running row of the one before —
+    Filterbank::mix_from) performs the single bank's operations in the single bank's order: bit-identical,
+    with and without the per-band distortion.  The full-size GPU tests lean on this to get the oracle's
+    own 4096- and 65,536-term sums in seconds."""
+    import oracle
+    from conftest import make_resonator, oracle_chained
+    N, L = 301, 6000
+    x = (20.0 * design.white_noise(L)).astype(dtype)
+    for dist in (0, 1):
+        whole = make_resonator(oracle.Filterbank, N, dtype, mode=mode, k_p=0.01, k_g=0.05).process(x, distortion=dist)
+        for parts in (1, 2, 7):
+            got = oracle_chained(N, dtype, x, mode=mode, partitions=parts, distortion=dist, k_p=0.01, k_g=0.05)
+            assert np.array_equal(got, whole)
