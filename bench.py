@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's filters are split over the GPUs (BASELINE configs[2]) instead of N filters per GPU")
     ap.add_argument("--followers", default="replica", choices=["ring", "replica"], help="with --env: how y[t-width] is obtained (HBM ring, or lagged replica filters)")
     ap.add_argument("--sum", default="ordered", choices=["ordered", "tree"], help="mixdown: ordered = the reference's index order and rounding (bit-identical, default); tree = per-CTA partial sums (tolerance mode)")
+    ap.add_argument("--exchange", default="chain", choices=["chain", "reduce"], help="N > 1, filter-partitioned: chain = the running bank-sum row crosses the GPUs in filter order (bit-identical to one bank); reduce = ncclReduce of order-free partial sums")
+    ap.add_argument("--parity-samples", type=int, default=48000, help="prefix of the block checked against the oracle's own sequential sum (0: skip)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the configs[2] strong-scaling block")
     ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
 
@@ -84,6 +87,47 @@ def make_bank(cls, w, rank, world, dtype, **kw):
     fb.mix(gains)
     fb.boost(np.ones(w["N"]))
     return fb
+
+
+def make_comm(rank, world, local):
+    """hg_comm over the ranks of this torchrun job: rank 0's ncclUniqueId travels by torch.distributed"""
+    import torch
+    import torch.distributed as dist
+    import huygens_b200 as hb
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(hb.Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0)
+    return hb.Comm(world, rank, bytes(uid.cpu().numpy().tobytes()), device=local)
+
+
+def oracle_prefix(w, world, dtype, x, threads=None):
+    """the oracle's own sequential bank sum of the WHOLE bank (all ranks' filters) over a prefix of the input:
+    consecutive filter partitions chained on the host threads (oracle.chained_sum — the single bank's operations in
+    the single bank's order)"""
+    import oracle
+    oracle.build()
+    threads = threads or min(os.cpu_count() or 1, 32)
+    ntot = w["N"] * world
+    fwd, back, gains = bank_params(dict(w, N=ntot), 0, 1)
+    banks = []
+    for idx in np.array_split(np.arange(ntot), min(threads, ntot)):
+        fb = oracle.Filterbank(2, len(idx), w["k_p"], w["k_g"], dtype=dtype, mode="strict")
+        for j, n in enumerate(idx):
+            fb.coefficients(j, fwd[n], back[n])
+        fb.mix(gains[idx])
+        fb.boost(np.ones(len(idx)))
+        banks.append(fb)
+    return oracle.chained_sum(banks, x)
+
+
+def parity_block(got, ref, what):
+    a, b = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    peak = float(np.max(np.abs(b))) or 1.0
+    err = float(np.max(np.abs(a - b)))
+    den = float(np.sum((a - b) ** 2))
+    return {"vs": what, "samples": int(len(b)), "bit_identical": bool(np.array_equal(np.asarray(got), np.asarray(ref))),
+            "max_abs_err_rel_peak": err / peak, "snr_db": None if den == 0 else float(10 * np.log10(np.sum(b * b) / den))}
 
 
 def synth_input(w, L, dtype):
@@ -320,6 +364,78 @@ def run_c5(args, w, rank, world, local):
         dist.destroy_process_group()
 
 
+def strong_c3(args, rank, world, local, comm, flush):
+    """BASELINE configs[2]: Filterbank<float> of 65,536 filters partitioned over the GPUs, one block of 10 s.
+    Times the chain exchange (bit-identical) and the ncclReduce exchange, and — on rank 0 alone — the whole bank on
+    one GPU, all in this run; parity of both exchanges against the oracle's sequential sum on a prefix."""
+    import torch
+    import torch.distributed as dist
+    import huygens_b200 as hb
+    w = dict(WORKLOADS["c3"])
+    ntot, L = w["N"], int(w["seconds"] * SR)
+    if ntot % world:
+        return {"skipped": f"{ntot} filters do not split over {world} GPUs"}
+    w["N"] = ntot // world
+    x_np = synth_input(w, L, np.float32)
+    x = torch.from_numpy(x_np).cuda()
+    root = world - 1
+    out = torch.empty(L, dtype=torch.float32, device="cuda")
+    res = {"workload": f"Filterbank<float> {ntot} filters over {world} GPUs ({w['N']} per GPU), {w['seconds']} s 48 kHz chirp, summed output",
+           "filters_total": ntot, "samples": L}
+    n_par = min(L, 24000)
+    ref = oracle_prefix(w, world, np.float32, x_np[:n_par]) if rank in (0, root) else None
+    for mode in ("chain", "reduce"):
+        fb = make_bank(hb.Filterbank, w, rank, world, np.float32, arith=args.arith, device=local)
+        dst = world - 1 if mode == "chain" else 0
+        for _ in range(3):
+            fb.process_sharded(comm, x, out=out if rank == dst else None, mode=mode)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            dist.barrier()
+            ev[i][0].record()
+            fb.process_sharded(comm, x, out=out if rank == dst else None, mode=mode)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # parity: a fresh bank renders the prefix (the timed bank's state has moved on)
+        fbp = make_bank(hb.Filterbank, w, rank, world, np.float32, arith=args.arith, device=local)
+        fbp.process_sharded(comm, x[:n_par].contiguous(), out=out[:n_par] if rank == dst else None, mode=mode)
+        torch.cuda.synchronize()
+        box = [parity_block(out[:n_par].cpu().numpy(), ref, f"oracle sequential sum of all {ntot} filters, first {n_par} samples") if rank == dst else None]
+        dist.broadcast_object_list(box, src=dst)
+        info = fb.last_launch()
+        res[mode] = {"ms_per_block": t.item() * 1e3, "value": float(ntot) * L / t.item(), "unit": "filter-samples/s",
+                     "kernel": {0: "K1-ws", -2: "K1-ru"}.get(info["filters_per_thread"], "K1 lanes"), "ctas_per_gpu": info["ctas"], "parity": box[0]}
+        del fb, fbp
+    # the same bank on ONE GPU (rank 0 alone, the others wait)
+    one = [None]
+    if rank == 0:
+        w1 = dict(WORKLOADS["c3"])
+        fb1 = make_bank(hb.Filterbank, w1, 0, 1, np.float32, arith=args.arith, device=local)
+        for _ in range(3):
+            fb1.process(x, out=out)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            fb1.process(x, out=out)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        one[0] = sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / args.steps
+        del fb1
+    dist.barrier()
+    dist.broadcast_object_list(one, src=0)
+    res["one_gpu_ms_per_block"] = one[0] * 1e3
+    for mode in ("chain", "reduce"):
+        res[mode]["speedup_vs_one_gpu"] = one[0] * 1e3 / res[mode]["ms_per_block"]
+        res[mode]["efficiency"] = res[mode]["speedup_vs_one_gpu"] / world
+    return res
+
+
 def workload_config(w, args, world):
     tname = "double" if w.get("dtype") == "f64" else "float"
     sname = f"{w['streams']} streams x " if w.get("streams", 1) > 1 else ""
@@ -371,19 +487,23 @@ def main():
     chain_cycles = hb.chain_latency(dtype, device=local)
 
     env_buf = torch.empty((S, L // 64, N), dtype=tdtype, device="cuda") if args.env else None
+    exchange = world > 1 and S == 1            # filter-partitioned: the running row crosses the GPUs; stream-partitioned: no exchange
+    comm = make_comm(rank, world, local) if exchange else None
+    shard_mode = "reduce" if args.exchange == "reduce" else "chain"
+    root = world - 1 if shard_mode == "chain" else 0      # where the finished bank sum lands
 
     def render(xi, oi):
         if args.env:
             fb.process_env(xi, width=2400, hop=64, out=oi, env=env_buf, followers=args.followers)
+        elif exchange:
+            # one kernel per GPU; in chain mode the last CTA of rank r hands the running row to rank r+1 through
+            # peer memory (hg_fb_process_sharded), in reduce mode ncclReduce adds the ranks' partial sums
+            fb.process_sharded(comm, xi, out=oi, mode=shard_mode)
         else:
             fb.process(xi, out=oi, mode=args.mode)
 
-    exchange = world > 1 and S == 1            # filter-partitioned: one reduce of the partial sums; stream-partitioned: none
-
     def step():
         render(x, out)
-        if exchange:
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -398,34 +518,56 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                    # L2 flush, outside the timed events
+        if world > 1:
+            dist.barrier()                       # the ranks of a chain start a block together
         ev[i][0].record()
-        kev[i][0].record()
         render(x, out)
-        kev[i][1].record()
-        if exchange:
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
         ev[i][1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_total = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
+    t_kernel = t_total
     if world > 1:
-        tt = torch.tensor([t_total, t_kernel], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_total, t_kernel = tt.tolist()
+        t_total = t_kernel = tt.item()
+
+    # parity: a fresh bank (zero state, like the oracle's) renders a prefix of the block through the same path; the
+    # result is compared with the oracle's own sequential sum of the WHOLE bank (all ranks' filters)
+    parity = None
+    n_par = min(L, args.parity_samples)
+    if n_par > 0 and not args.env and args.mode == "exact" and S == 1:
+        fbp = make_bank(hb.Filterbank, w, rank, world, dtype, arith=args.arith, device=local, sum_mode=args.sum)
+        xp = x[:n_par].contiguous()
+        if exchange:
+            fbp.process_sharded(comm, xp, out=out[:n_par] if rank == root else None, mode=shard_mode)
+        else:
+            fbp.process(xp, out=out[:n_par], mode=args.mode)
+        torch.cuda.synchronize()
+        if rank == root:
+            ref = oracle_prefix(w, world, dtype, x_host.numpy()[:n_par])
+            parity = parity_block(out[:n_par].cpu().numpy(), ref,
+                                  f"oracle (strict, sequential index-order sum of all {N * world} filters), first {n_par} samples")
+        del fbp
+    if world > 1:
+        box = [parity]
+        dist.broadcast_object_list(box, src=root)
+        parity = box[0]
 
     # end to end through the public API with host buffers (H2D + D2H inside the call)
-    xh, oh = x_host.numpy(), out_host.numpy()
+    xh = x_host.numpy()
+    oh = out_host.numpy() if (not exchange or rank == root) else None
     env_h = torch.empty(env_buf.shape, dtype=tdtype).pin_memory().numpy() if args.env else None
 
     def render_host():
         if args.env:
             fb.process_env(xh, width=2400, hop=64, out=oh, env=env_h, followers=args.followers)   # envelopes come back to the host too
+        elif exchange:
+            fb.process_sharded(comm, xh, out=oh, mode=shard_mode)      # every rank uploads the block; the root downloads the sum
         else:
             fb.process(xh, out=oh, mode=args.mode)
 
@@ -437,16 +579,16 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         render_host()                                # synchronises before returning
-        if exchange:
-            # partial sums meet on rank 0: host -> device -> reduce would double count copies; the
-            # device-side reduce of the staged output is what a sharded caller does
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     if world > 1:
         tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = tt.item()
+
+    # N > 1: BASELINE configs[2] — 65,536 filters split over the GPUs (strong scaling), chain and reduce exchange,
+    # against the same bank on one GPU measured in this run, with parity against the oracle on a prefix
+    strong = strong_c3(args, rank, world, local, comm, flush) if (exchange and args.workload == "c2" and not args.no_strong) else None
 
     # side measurement (N = 1 only): the same block through the time-parallel scan, whose result is
     # tolerance-bounded instead of bit-identical
@@ -526,6 +668,13 @@ def main():
         line["roofline"].update({"achieved": per_gpu_kernel * slots / 1e12, "frac": per_gpu_kernel * slots / peak["slots_per_s"],
                                  "frac_of_nominal": per_gpu_kernel * slots / nominal, "slots_per_unit": slots,
                                  "note": "Filterbank + per-band RMSbank(2400) followers; y[t-2400] regenerated by lagged replica filters (no ring); envelopes every 64 samples"})
+    if parity:
+        line["parity"] = parity
+    if strong:
+        line["strong_c3"] = strong
+    if exchange:
+        line["config"]["exchange"] = ("running bank-sum row handed GPU to GPU through peer memory in filter order (hg_fb_process_sharded, HG_SHARD_CHAIN); result on the last rank"
+                                      if shard_mode == "chain" else "ncclReduce of the ranks' partial sums (HG_SHARD_REDUCE)")
     if scan_info:
         line["scan"] = scan_info
     if not args.no_cpu_baseline:

@@ -8,4 +8,4 @@ host mirror used by the tests and bench.py.
 """
 from . import design  # noqa: F401
 from ._lib import HuygensError, LIB_PATH, build, lib  # noqa: F401
-from .banks import Filterbank, Latchbank, Oscbank, RMSbank, Slidebank, Stickbank, chain_latency, fma_peak  # noqa: F401
+from .banks import Comm, Filterbank, Latchbank, Oscbank, RMSbank, Slidebank, Stickbank, chain_latency, fma_peak  # noqa: F401

@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(_HERE, "lib", "libhuygens_cuda.so")   # HG_LIB_PATH: experiment builds
 _LIB = None
 
-HG_OK, HG_ERR_INVALID, HG_ERR_UNSUPPORTED, HG_ERR_CUDA, HG_ERR_NOMEM = 0, 1, 2, 3, 4
+HG_OK, HG_ERR_INVALID, HG_ERR_UNSUPPORTED, HG_ERR_CUDA, HG_ERR_NOMEM, HG_ERR_NCCL = 0, 1, 2, 3, 4, 5
+HG_SHARD_CHAIN, HG_SHARD_REDUCE = 0, 1
 HG_F32, HG_F64 = 0, 1
 HG_ARITH_STRICT, HG_ARITH_FMA = 0, 1
 HG_MODE_AUTO, HG_MODE_EXACT, HG_MODE_SCAN = 0, 1, 2
@@ -44,6 +45,13 @@ SYMBOLS = [
     ("hg_fb_set_sum_mode", _i, [_vp, _i]),
     ("hg_fb_check", _i, [_vp]),
     ("hg_fb_debug_profile", _i, [_vp, _vp, _i]),
+    ("hg_comm_get_unique_id", _i, [_vp]),
+    ("hg_comm_init_rank", _i, [C.POINTER(_vp), _i, _i, _vp, _i]),
+    ("hg_comm_init_all", _i, [C.POINTER(_vp), _i, _pi]),
+    ("hg_comm_destroy", _i, [_vp]),
+    ("hg_comm_rank", _i, [_vp]),
+    ("hg_comm_size", _i, [_vp]),
+    ("hg_fb_process_sharded", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_osc_create", _i, [C.POINTER(_vp), _i, _i, _i, _i]),
     ("hg_osc_destroy", _i, [_vp]),
     ("hg_osc_freqmod", _i, [_vp, _i, _d]),

@@ -149,6 +149,27 @@ class Filterbank(_Handle):
             return out, bd
         return out
 
+    def process_sharded(self, comm, x, out=None, mode="chain", root=-1):
+        """Collective render of a filter-partitioned bank (hg_fb_process_sharded): this handle holds rank
+        comm.rank's consecutive slice of the filters, every rank passes the same input.  mode "chain" keeps the
+        reference's index-order sum across the GPUs (bit-identical to one bank; result on the last rank unless `root`
+        says otherwise), "reduce" adds order-free partial sums with ncclReduce (result on rank 0).  Returns `out` on
+        the root rank, None elsewhere."""
+        m = {"chain": L.HG_SHARD_CHAIN, "reduce": L.HG_SHARD_REDUCE}[mode]
+        eff_root = root if root >= 0 else (comm.size - 1 if m == L.HG_SHARD_CHAIN else 0)
+        if _is_torch(x):
+            import torch
+            Ls, stream = x.shape[-1], _torch_stream()
+            if out is None and comm.rank == eff_root:
+                out = torch.empty_like(x)
+        else:
+            x = np.ascontiguousarray(x, dtype=self.dtype)
+            Ls, stream = x.shape[-1], None
+            if out is None and comm.rank == eff_root:
+                out = np.empty_like(x)
+        L.check(L.lib().hg_fb_process_sharded(self._h, comm._h, _ptr(x), _ptr(out) if comm.rank == eff_root else None, Ls, m, root, stream))
+        return out if comm.rank == eff_root else None
+
     def process_env(self, x, width=2400, hop=64, out=None, env=None, followers=None):
         """Block render + one RMSbank(width) envelope follower per (stream, filter), fused on the device.
         Returns (out_sum, env[streams][L // hop][N]); env rows are block samples hop-1, 2*hop-1, ...
@@ -246,6 +267,43 @@ class Filterbank(_Handle):
         m, n, f, g = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         L.check(L.lib().hg_fb_last_launch(self._h, C.byref(m), C.byref(n), C.byref(f), C.byref(g)))
         return dict(mode={1: "exact", 2: "scan"}.get(m.value, "none"), launches=n.value, filters_per_thread=f.value, ctas=g.value)
+
+
+class Comm:
+    """One rank of a filter-partitioned group of GPUs (hg_comm): `Comm.unique_id()` on rank 0, shared with the
+    other ranks by any means (e.g. a torch.distributed broadcast), then `Comm(n_ranks, rank, uid, device)` on
+    every rank; or `Comm.init_all(n)` in one process that drives several GPUs."""
+
+    def __init__(self, n_ranks, rank, uid, device=0, _handle=None):
+        self._h = C.c_void_p() if _handle is None else _handle
+        if _handle is None:
+            buf = (C.c_ubyte * 128).from_buffer_copy(bytes(uid))
+            L.check(L.lib().hg_comm_init_rank(C.byref(self._h), int(n_ranks), int(rank), C.cast(buf, C.c_void_p), int(device)))
+        self.rank, self.size = L.lib().hg_comm_rank(self._h), L.lib().hg_comm_size(self._h)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        L.check(L.lib().hg_comm_get_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    @staticmethod
+    def init_all(n_devices, devices=None):
+        hs = (C.c_void_p * n_devices)()
+        dv = None if devices is None else (C.c_int * n_devices)(*devices)
+        L.check(L.lib().hg_comm_init_all(hs, n_devices, dv))
+        return [Comm(n_devices, i, None, _handle=C.c_void_p(hs[i])) for i in range(n_devices)]
+
+    def close(self):
+        if self._h:
+            L.lib().hg_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Oscbank(_Handle):

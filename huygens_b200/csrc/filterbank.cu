@@ -467,6 +467,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
     const bool ordered = fb->sum_mode != 0 || peer || fb->cur_carry_in;
     const int rows = ordered ? 1 : groups;   // partial-sum rows that reach HBM
     HG_TRY(chain_reserve(fb, ordered && summing ? (size_t)groups * fb->S : 1, st));
+    if (peer && fb->chain_ring_log2 != 11) return fail(HG_ERR_UNSUPPORTED, "sharded rendering: the bank has too many chain links for the peer ring size");
     // segment the block so the partial-sum scratch stays bounded
     size_t seg = L;
     if (rows > 1 && d_out) {

@@ -176,7 +176,7 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     if (fb->env_mode == HG_ENV_REPLICA && fb->d_rms_sum && !fb->cur_env)
         return hg::fail(HG_ERR_INVALID, "hg_fb_process: replica followers are running and must see every tick; render through hg_fb_process_env");
     if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
-    if (!out_sum && !out_bands) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
+    if (!out_sum && !out_bands && !fb->cur_peer.outbox) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
     HG_CUDA(cudaSetDevice(fb->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;   // NULL = the legacy default stream, as in the CUDA runtime
     const size_t es = hg::dtype_size(fb->dtype);

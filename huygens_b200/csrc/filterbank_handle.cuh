@@ -52,6 +52,7 @@ struct hg_fb {
     // the chain's ends for the block being processed (set by the sharded entry points, else null)
     const void* cur_carry_in = nullptr;    // [S][L] running row to start from (null: zero)
     hg::chain::Params cur_peer = {};       // inbox / outbox of a multi-GPU chain (ring, credit fields unused)
+    const void* chain_owner = nullptr;     // the hg_comm whose position sequence the rings last carried (null: the handle's own)
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
     int ws_level = 0;

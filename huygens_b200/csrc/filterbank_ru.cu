@@ -722,6 +722,8 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             out_row = ordered ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)cta * P.S + s) * (size_t)L);   // tree mode: one partial row per CTA
         const T* carry = (ordered && first && head && !has_in && P.carry_in) ? P.carry_in + (size_t)s * P.carry_stride : nullptr;
         const int dist = P.dist;
+        // every RU warp this S warp serves is a full group of 32 filters (and there is at least one)
+        const bool fast_rows = wa < wb && (w_first + wb) * 32 <= N;
         int yb = 0;
         unsigned ypar = 0;
         long long pf_in = 0, pf_y = 0, pf_mix = 0, pf_out = 0;
@@ -733,6 +735,67 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             const int pb = k % PD;
             const unsigned ppar = (unsigned)((k / PD) & 1);
             long long pc0 = HG_PROF_ON(P) ? clock64() : 0, pc1;
+            if (VF && sizeof(T) == 4 && GPS == 2 && fast_rows && !dist) {
+                // Steady state of the VF tiles (float): fetch the terms of both RU warps into registers and give the tile
+                // slots back BEFORE waiting for the running row — the RU warps are then never held up by the chain's
+                // latency, and the chain's stage is nothing but the hand-over and the 64-deep FADD chain.
+                float v0[32], v1[32];
+                const bool two = wa + 1 < wb;
+                mbar_wait(&y_full[wa * NB + yb], ypar);
+                {
+                    const float* vr = reinterpret_cast<const float*>(ytiles) + ((size_t)wa * NB + yb) * 32 * RS + lane * RS;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) ld4<float>(vr + 4 * q, *reinterpret_cast<float(*)[4]>(&v0[4 * q]));
+                }
+                if (two) {
+                    mbar_wait(&y_full[(wa + 1) * NB + yb], ypar);
+                    const float* vr = reinterpret_cast<const float*>(ytiles) + ((size_t)(wa + 1) * NB + yb) * 32 * RS + lane * RS;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) ld4<float>(vr + 4 * q, *reinterpret_cast<float(*)[4]>(&v1[4 * q]));
+                }
+                // the slots are free once every lane's loads have returned (the empty asm makes the arrive wait for them)
+                asm volatile("" ::"f"(v0[31]), "f"(two ? v1[31] : v0[30]) : "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&y_empty[wa * NB + yb]);
+                    if (two) mbar_arrive(&y_empty[(wa + 1) * NB + yb]);
+                }
+                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_y += pc1 - pc0; pc0 = pc1; }
+                float a = 0.f;
+                if (summing) {
+                    if (smem_in) {
+                        mbar_wait(&ps_full[in_link * PD + pb], ppar);
+                        a = reinterpret_cast<const float*>(psum)[((size_t)in_link * PD + pb) * 32 + lane];
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ps_empty[in_link * PD + pb]);
+                    } else if (carry) {
+                        if (lane < tn) a = (float)carry[tg + lane];
+                    }
+                    if (HG_PROF_ON(P)) { pc1 = clock64(); pf_in += pc1 - pc0; pc0 = pc1; }
+#pragma unroll
+                    for (int l = 0; l < 32; l++) a = __fadd_rn(v0[l], a);                  // filterbank.h:130, index order
+                    if (two) {
+#pragma unroll
+                        for (int l = 0; l < 32; l++) a = __fadd_rn(v1[l], a);
+                    }
+                    if (HG_PROF_ON(P)) { pc1 = clock64(); pf_mix += pc1 - pc0; pc0 = pc1; }
+                    if (!last) {
+                        mbar_wait(&ps_empty[sidx * PD + pb], ppar ^ 1u);
+                        reinterpret_cast<float*>(psum)[((size_t)sidx * PD + pb) * 32 + lane] = a;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ps_full[sidx * PD + pb]);
+                    } else if (pout.on()) {
+                        pout.reserve(C, tg + TILE);
+                        T a1v[1] = {(T)a};
+                        pout.send(C, tg + lane, a1v);
+                    } else if (out_row) {
+                        if (lane < tn) out_row[tg + lane] = (T)a;
+                    }
+                    if (HG_PROF_ON(P)) pf_out += clock64() - pc0;
+                }
+                if (++yb == NB) { yb = 0; ypar ^= 1u; }
+                continue;
+            }
             if (summing) {
                 if (smem_in) {
                     // running row after the filters before this S warp's (left by S warp sidx-1, or by the gateway)

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 typedef int hg_status;
-enum { HG_OK = 0, HG_ERR_INVALID = 1, HG_ERR_UNSUPPORTED = 2, HG_ERR_CUDA = 3, HG_ERR_NOMEM = 4 };
+enum { HG_OK = 0, HG_ERR_INVALID = 1, HG_ERR_UNSUPPORTED = 2, HG_ERR_CUDA = 3, HG_ERR_NOMEM = 4, HG_ERR_NCCL = 5 };
 enum { HG_F32 = 0, HG_F64 = 1 };
 /* arithmetic mode: STRICT = every mul/add rounded separately (x86-64 g++ -O3 build of the
  * reference, tests/build.sh:8); FMA = the fixed contraction pattern of DESIGN.md §3. */
@@ -47,6 +47,7 @@ typedef struct hg_fb hg_fb;
 typedef struct hg_osc hg_osc;
 typedef struct hg_casc hg_casc;
 typedef struct hg_rms hg_rms;
+typedef struct hg_comm hg_comm;
 
 const char* hg_last_error(void);
 /* number of visible CUDA devices (0 if none / no driver); never fails */
@@ -148,6 +149,31 @@ hg_status hg_fb_check(hg_fb* fb);
  * counters of its S and R roles (waits for the y tile, for the running row, mixdown, hand-over; R's barrier waits and
  * total).  Copies [n_ctas][8] counters of the last launch (chain order).  Not part of the reference's surface. */
 hg_status hg_fb_debug_profile(hg_fb* fb, long long* counters, int n_ctas);
+
+/* ---- filter-partitioned rendering over the GPUs of one box (BASELINE configs[2]) ------------------------------ */
+/* new (nothing in the reference to match: it is single-threaded host code).  A bank of N filters is split over G
+ * ranks, rank r holding the filters [r N/G, (r+1) N/G) in an hg_fb of its own device; every rank renders the same
+ * input.  One rank per process: rank 0 calls hg_comm_get_unique_id (128 bytes, an ncclUniqueId), hands it to the
+ * others by any means, then every rank calls hg_comm_init_rank.  One process driving several GPUs (a C++ audio
+ * host): hg_comm_init_all fills comms[0..n_devices).  NCCL (libnccl.so.2, loaded at run time) bootstraps the group;
+ * neighbouring ranks map a small mailbox of each other's device memory (CUDA IPC / peer access over NVLink). */
+hg_status hg_comm_get_unique_id(void* id128);
+hg_status hg_comm_init_rank(hg_comm** out, int n_ranks, int rank, const void* id128, int device);
+hg_status hg_comm_init_all(hg_comm** comms, int n_devices, const int* devices /* NULL: 0..n-1 */);
+hg_status hg_comm_destroy(hg_comm* comm);
+int hg_comm_rank(const hg_comm* comm);
+int hg_comm_size(const hg_comm* comm);
+/* HG_SHARD_CHAIN: operator()'s index-order sum (src/filterbank.h:130) is kept across the devices — the running
+ *   bank-sum row leaves the last CTA of rank r for rank r+1 through peer memory, tile by tile under the compute, one
+ *   kernel per GPU; the result is bit-identical to one hg_fb of all N filters and lands on the last rank.
+ * HG_SHARD_REDUCE: every rank renders its own partial sum and one ncclReduce adds the rows (order-free: within
+ *   ~N eps of the reference sum). */
+enum { HG_SHARD_CHAIN = 0, HG_SHARD_REDUCE = 1 };
+/* Collective: every rank of `comm` calls it with its own handle, the same input block and L.  out_sum [L] is written
+ * on rank `root` only (root < 0: the last rank for CHAIN, rank 0 for REDUCE; a root other than the chain's tail costs
+ * one ncclSend/ncclRecv of the row); other ranks may pass NULL.  One stream per handle (n_streams == 1). */
+hg_status hg_fb_process_sharded(hg_fb* fb, hg_comm* comm, const void* in, void* out_sum, size_t L, int shard_mode,
+                                int root, void* cuda_stream);
 
 /* ---- Oscbank<T,N>  (src/oscbank.h, src/multichannel.h) ------------------------------------ */
 hg_status hg_osc_create(hg_osc** out, int dtype, int arith, int n_partials, int device);   /* oscbank.h:37-47 */
