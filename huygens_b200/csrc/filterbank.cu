@@ -384,6 +384,16 @@ static hg_status launch_k1(const FbK1Params<T>& P, int groups, cudaStream_t st) 
     if (P.tv_rows && P.tv_hop < K1_TVS) smem += sizeof(T) * (size_t)(K1_TVS + 1) * 7 * NT * F;
     auto kern = fb_exact_kernel<T, FMA, F, NT, BANDS>;
     if (smem > 48 * 1024) HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (P.chain.ordered && (P.out || P.chain.outbox)) {
+        // every CTA of a stream's chain must be resident at once (see fb_launch_exact_ru)
+        int per_sm = 0, dev = 0, sms = 0;
+        HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT + 32, smem));
+        HG_CUDA(cudaGetDevice(&dev));
+        HG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if ((long)groups > (long)per_sm * sms)
+            return fail(HG_ERR_UNSUPPORTED, "ordered mixdown (lane kernel): %d filters of one stream need %d CTAs, this GPU holds %d at once — select HG_SUM_TREE for this bank",
+                        P.N, groups, per_sm * sms);
+    }
     kern<<<dim3(groups, P.S), NT + 32, smem, st>>>(P);
     HG_CUDA(cudaGetLastError());
     return HG_OK;

@@ -947,6 +947,17 @@ static hg_status launch_ru(const FbRuParams<T>& Q, cudaStream_t st) {
     const size_t smem = ru::Layout<T>(Q.W, ENV == 2).bytes();
     auto kern = fb_exact_ru_kernel<T, FMA, BANDS, ENV>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (Q.k.chain.ordered && (Q.k.out || Q.k.chain.outbox)) {
+        // every CTA of a stream's chain must be resident at once: one that has not started yet would stall its
+        // predecessor for good once the link's ring is full
+        int per_sm = 0, dev = 0, sms = 0;
+        HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (Q.W + ru::s_warps(Q.W) + 1) * 32, smem));
+        HG_CUDA(cudaGetDevice(&dev));
+        HG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if ((long)Q.cps > (long)per_sm * sms)
+            return fail(HG_ERR_UNSUPPORTED, "ordered mixdown: %d filters of one stream need %d CTAs, this GPU holds %d at once — split the bank over GPUs (hg_fb_process_sharded) or select HG_SUM_TREE",
+                        Q.k.N, Q.cps, per_sm * sms);
+    }
     kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W) + 1) * 32, smem, st>>>(Q);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
