@@ -19,6 +19,7 @@ HG_MODE_AUTO, HG_MODE_EXACT, HG_MODE_SCAN = 0, 1, 2
 HG_FB_FIXED = 1
 HG_DIST_NONE, HG_DIST_SOFTCLIP = 0, 1
 HG_SUM_TREE, HG_SUM_ORDERED = 0, 1
+HG_EPI_NONE, HG_EPI_SOFTCLIP, HG_EPI_LIMITER = 0, 1, 2
 
 # every symbol include/huygens_cuda.h declares: (name, restype, argtypes)
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -37,6 +38,7 @@ SYMBOLS = [
     ("hg_fb_process", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_fb_process_env", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     ("hg_fb_set_follower_mode", _i, [_vp, _i]),
+    ("hg_fb_reset_followers", _i, [_vp]),
     ("hg_fb_process_events", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     ("hg_fb_process_tv", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     ("hg_fb_get_state", _i, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -44,6 +46,8 @@ SYMBOLS = [
     ("hg_fb_last_launch", _i, [_vp, _pi, _pi, _pi, _pi]),
     ("hg_fb_set_sum_mode", _i, [_vp, _i]),
     ("hg_fb_check", _i, [_vp]),
+    ("hg_fb_set_epilogue", _i, [_vp, _i, _d, _d]),
+    ("hg_fb_process_voice", _i, [_vp, _vp, _vp, _vp, _sz, _i, _vp]),
     ("hg_fb_debug_profile", _i, [_vp, _vp, _i]),
     ("hg_comm_get_unique_id", _i, [_vp]),
     ("hg_comm_init_rank", _i, [C.POINTER(_vp), _i, _i, _vp, _i]),

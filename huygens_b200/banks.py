@@ -86,6 +86,21 @@ class Filterbank(_Handle):
         (src/filterbank.h:130) — bit-identical sums; "tree": per-CTA partial sums added in a fixed tree order."""
         L.check(L.lib().hg_fb_set_sum_mode(self._h, {"ordered": L.HG_SUM_ORDERED, "tree": L.HG_SUM_TREE}[mode]))
 
+    def set_epilogue(self, kind=None, dry=0.0, width=0.9):
+        """Fused post-processing of the bank sum: kind "softclip" -> softclip(dry*in + sum, width)
+        (tests/filterbank.cpp:205-207), "limiter" -> 2/PI*atan(dry*in + sum) (src/wave.h:150), None -> off."""
+        k = {None: L.HG_EPI_NONE, "softclip": L.HG_EPI_SOFTCLIP, "limiter": L.HG_EPI_LIMITER}[kind]
+        L.check(L.lib().hg_fb_set_epilogue(self._h, k, float(dry), float(width)))
+
+    def process_voice(self, x, dry_in=None, distortion=0):
+        """out[t] = epilogue(dry * dry_in[t] + bank(x[t], distortion)) — tests/filterbank.cpp:200-215 in block form
+        (set_epilogue first).  Host arrays."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        d = None if dry_in is None else np.ascontiguousarray(dry_in, dtype=self.dtype)
+        out = np.empty_like(x)
+        L.check(L.lib().hg_fb_process_voice(self._h, _ptr(x), _ptr(d), _ptr(out), x.shape[-1], distortion, None))
+        return out
+
     def check(self):
         """Synchronous health check of the ordered mixdown (raises if its watchdog fired)."""
         L.check(L.lib().hg_fb_check(self._h))
@@ -173,7 +188,7 @@ class Filterbank(_Handle):
     def process_env(self, x, width=2400, hop=64, out=None, env=None, followers=None):
         """Block render + one RMSbank(width) envelope follower per (stream, filter), fused on the device.
         Returns (out_sum, env[streams][L // hop][N]); env rows are block samples hop-1, 2*hop-1, ...
-        followers = "ring" (default) or "replica" (no ring traffic, ~2x faster; every tick must then be rendered
+        followers = "replica" (default: no ring traffic, ~2x faster) or "ring"; either way every tick must then be rendered
         through process_env), chosen at the first call."""
         if followers is not None:
             L.check(L.lib().hg_fb_set_follower_mode(self._h, {"ring": 1, "replica": 2}[followers]))

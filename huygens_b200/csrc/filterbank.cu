@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(NT + 32) fb_exact_kernel(FbK1Params<T> P) {
                     T a1v[1] = {acc};
                     pout.send(C, tg + lane, a1v);
                 } else if (out_row) {
-                    if (lane < tn) out_row[tg + lane] = acc;
+                    if (lane < tn) {
+                        if (P.epi.kind && ordered) acc = epilogue_dev<T>(P.epi, acc, P.dry_in[(size_t)s * P.in_stride + tg + lane]);
+                        out_row[tg + lane] = acc;
+                    }
                 }
                 if (pin.on()) {
                     __syncwarp();
@@ -369,13 +372,23 @@ __global__ void __launch_bounds__(NT + 32) fb_exact_kernel(FbK1Params<T> P) {
 // out[s][t] = sum_g partial[g][s][t], fixed order -> deterministic
 template <typename T>
 __global__ void __launch_bounds__(256) fb_reduce_partials(const T* __restrict__ partial, T* __restrict__ out,
-                                                          int groups, int S, long L, long out_stride) {
+                                                          int groups, int S, long L, long out_stride,
+                                                          Epilogue epi, const T* __restrict__ in, long in_stride) {
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
     const int s = blockIdx.y;
     if (i >= L) return;
     T sum = (T)0;
     for (int g = 0; g < groups; g++) sum += partial[((size_t)g * S + s) * (size_t)L + i];
+    if (epi.kind) sum = epilogue_dev<T>(epi, sum, in[(size_t)s * in_stride + i]);
     out[(size_t)s * out_stride + i] = sum;
+}
+
+// tree mode with a single row (the kernels wrote out[] themselves): the epilogue as a pass of its own
+template <typename T>
+__global__ void __launch_bounds__(256) fb_epilogue_pass(T* __restrict__ out, long out_stride, long L, Epilogue epi, const T* __restrict__ in, long in_stride) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i < L) out[(size_t)s * out_stride + i] = epilogue_dev<T>(epi, out[(size_t)s * out_stride + i], in[(size_t)s * in_stride + i]);
 }
 
 template <typename T, bool FMA, int F, int NT, bool BANDS>
@@ -532,6 +545,8 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.bands_vec = (vec_ok && (t0 % 4 == 0)) ? 1 : 0;
         P.taps = fb->taps;
         P.dist = fb->cur_dist;
+        P.epi = fb->epi;
+        P.dry_in = (fb->cur_dry_in ? (const T*)fb->cur_dry_in : d_in) + t0;
         P.chain = fb->cur_peer;
         P.chain.ring = (unsigned long long*)fb->d_chain_ring;
         P.chain.credit = fb->d_chain_credit;
@@ -579,7 +594,12 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         fb->ticket_base += (unsigned)fb->last_ctas;
         if (!P.direct && d_out) {
             dim3 grid((unsigned)((len + 255) / 256), fb->S);
-            fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, rows, fb->S, (long)len, (long)L);
+            fb_reduce_partials<T><<<grid, 256, 0, st>>>((const T*)fb->partial.p, d_out + t0, rows, fb->S, (long)len, (long)L, P.epi, P.dry_in, (long)L);
+            HG_CUDA(cudaGetLastError());
+            fb->last_launches++;
+        } else if (!ordered && d_out && P.epi.kind) {
+            dim3 grid((unsigned)((len + 255) / 256), fb->S);
+            fb_epilogue_pass<T><<<grid, 256, 0, st>>>(d_out + t0, (long)L, (long)len, P.epi, P.dry_in, (long)L);
             HG_CUDA(cudaGetLastError());
             fb->last_launches++;
         }

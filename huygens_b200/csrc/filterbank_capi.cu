@@ -54,9 +54,12 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     if (!fb) return hg::fail(HG_ERR_NOMEM, "hg_fb_create: host allocation failed");
     fb->dtype = dtype; fb->arith = arith; fb->order = order; fb->N = n_filters; fb->S = n_streams;
     fb->flags = flags; fb->device = device;
-    cudaDeviceProp prop;
-    HG_CUDA(cudaGetDeviceProperties(&prop, device));
-    fb->sm_count = prop.multiProcessorCount;
+    int sm_count__ = 0;
+    {
+        const cudaError_t pe = cudaDeviceGetAttribute(&sm_count__, cudaDevAttrMultiProcessorCount, device);
+        if (pe != cudaSuccess) { hg_fb_destroy(fb); return hg::fail(HG_ERR_CUDA, "hg_fb_create: cudaDeviceGetAttribute -> %s", cudaGetErrorString(pe)); }
+    }
+    fb->sm_count = sm_count__;
     const double sp = relaxation(k_p), sg = relaxation(k_g);
     if (dtype == HG_F32) {
         float fsp = (float)sp, fsg = (float)sg;
@@ -105,6 +108,7 @@ hg_status hg_fb_destroy(hg_fb* fb) {
     if (fb->d_ticket) cudaFree(fb->d_ticket);
     if (fb->d_chain_error) cudaFree(fb->d_chain_error);
     if (fb->d_prof) cudaFree(fb->d_prof);
+    fb->dry_stage.release();
     fb->in_stage.release(); fb->out_stage.release(); fb->bands_stage.release(); fb->partial.release();
     fb->scan_a.release(); fb->scan_b.release(); fb->env_stage.release();
     if (fb->d_rms_sum) cudaFree(fb->d_rms_sum);
@@ -173,8 +177,8 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     fb->cur_dist = distortion;
     fb->last_launches = 0;
     if (L == 0) return HG_OK;
-    if (fb->env_mode == HG_ENV_REPLICA && fb->d_rms_sum && !fb->cur_env)
-        return hg::fail(HG_ERR_INVALID, "hg_fb_process: replica followers are running and must see every tick; render through hg_fb_process_env");
+    if (fb->d_rms_sum && !fb->cur_env)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_process: the handle's envelope followers are running and must see every tick (their window would skip this block); render through hg_fb_process_env, or call hg_fb_reset_followers first");
     if (!in) return hg::fail(HG_ERR_INVALID, "hg_fb_process: null input");
     if (!out_sum && !out_bands && !fb->cur_peer.outbox) return hg::fail(HG_ERR_INVALID, "hg_fb_process: no output requested");
     HG_CUDA(cudaSetDevice(fb->device));
@@ -242,6 +246,10 @@ hg_status hg_fb_process(hg_fb* fb, const void* in, void* out_sum, void* out_band
     }
     if (use == HG_MODE_SCAN && out_bands)
         return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: scan mode renders the bank sum only");
+    if (use == HG_MODE_SCAN && fb->smoothers_custom)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: scan mode assumes the streams share their smoothed-gain state; hg_fb_set_state gave them their own");
+    if (use == HG_MODE_SCAN && fb->epi.kind)
+        return hg::fail(HG_ERR_UNSUPPORTED, "hg_fb_process: the fused epilogue needs the exact mode");
     fb->last_mode = use;
     hg_status rc;
     if (use == HG_MODE_EXACT) {
@@ -285,6 +293,36 @@ hg_status hg_fb_debug_profile(hg_fb* fb, long long* out, int n_ctas) {
     return HG_OK;
 }
 
+hg_status hg_fb_process_voice(hg_fb* fb, const void* in, const void* dry_in, void* out_sum, size_t L, int distortion, void* cuda_stream) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_process_voice: null handle");
+    if (L == 0) return HG_OK;
+    if (!in || !out_sum) return hg::fail(HG_ERR_INVALID, "hg_fb_process_voice: null in/out_sum");
+    HG_CUDA(cudaSetDevice(fb->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t bytes = (size_t)fb->S * L * hg::dtype_size(fb->dtype);
+    fb->cur_dry_in = nullptr;
+    if (dry_in && dry_in != in) {
+        if (hg::is_device_ptr(dry_in)) fb->cur_dry_in = dry_in;
+        else {
+            HG_TRY(fb->dry_stage.reserve(bytes));
+            HG_CUDA(cudaMemcpyAsync(fb->dry_stage.p, dry_in, bytes, cudaMemcpyHostToDevice, st));
+            fb->cur_dry_in = fb->dry_stage.p;
+        }
+    }
+    hg_status rc = hg_fb_process(fb, in, out_sum, nullptr, L, HG_MODE_EXACT, distortion, cuda_stream);
+    if (fb->cur_dry_in == fb->dry_stage.p && rc == HG_OK) rc = cudaStreamSynchronize(st) == cudaSuccess ? HG_OK : hg::fail(HG_ERR_CUDA, "hg_fb_process_voice: stream synchronise failed");
+    fb->cur_dry_in = nullptr;
+    return rc;
+}
+
+hg_status hg_fb_set_epilogue(hg_fb* fb, int kind, double dry, double width) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_epilogue: null handle");
+    if (kind != HG_EPI_NONE && kind != HG_EPI_SOFTCLIP && kind != HG_EPI_LIMITER) return hg::fail(HG_ERR_INVALID, "hg_fb_set_epilogue: bad kind %d", kind);
+    if (kind == HG_EPI_SOFTCLIP && !(width > 0.0 && width < 1.0)) return hg::fail(HG_ERR_INVALID, "hg_fb_set_epilogue: softclip width must be in (0, 1)");
+    fb->epi.kind = kind; fb->epi.dry = dry; fb->epi.width = width;
+    return HG_OK;
+}
+
 hg_status hg_fb_set_sum_mode(hg_fb* fb, int mode) {
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_sum_mode: null handle");
     if (mode != HG_SUM_ORDERED && mode != HG_SUM_TREE) return hg::fail(HG_ERR_INVALID, "hg_fb_set_sum_mode: bad mode %d", mode);
@@ -306,17 +344,28 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
     const size_t es = hg::dtype_size(fb->dtype), S = fb->S, N = fb->N;
     if (!fb->d_rms_sum) {
         // RMSbank(width) per (stream, filter): running sums zeroed (rmsbank.h:34-44) and either the ring of the
-        // last `width` squares (zeroed) or the lagged replicas (state of the filters now, idle for `width` ticks)
-        cudaError_t ce;
-        if ((ce = cudaMalloc(&fb->d_rms_sum, S * N * es)) != cudaSuccess)
-            return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower sums: %s", cudaGetErrorString(ce));
+        // last `width` squares (zeroed) or the lagged replicas (state of the filters now, idle for `width` ticks).
+        // Allocate into locals and commit only when everything succeeded: a half-initialised handle would launch
+        // the follower kernels on null buffers at the next call.
+        void *sum = nullptr, *lag_state = nullptr, *lag_par = nullptr, *xhist = nullptr, *ring = nullptr;
+        const size_t H = (size_t)width + 4;
+        const size_t ring_bytes = S * (size_t)width * ((N + 31) / 32 * 32) * es;
+        cudaError_t ce = cudaMalloc(&sum, S * N * es);
+        if (ce == cudaSuccess && fb->env_mode == 2) {
+            if ((ce = cudaMalloc(&lag_state, 3 * S * N * es)) == cudaSuccess && (ce = cudaMalloc(&lag_par, 7 * N * es)) == cudaSuccess)
+                ce = cudaMalloc(&xhist, S * H * es);
+        } else if (ce == cudaSuccess) {
+            ce = cudaMalloc(&ring, ring_bytes);
+        }
+        if (ce != cudaSuccess) {
+            cudaFree(sum); cudaFree(lag_state); cudaFree(lag_par); cudaFree(xhist); cudaFree(ring);
+            cudaGetLastError();
+            return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower state (%s mode, %zu bytes of ring): %s",
+                            fb->env_mode == 2 ? "replica" : "ring", fb->env_mode == 2 ? (size_t)0 : ring_bytes, cudaGetErrorString(ce));
+        }
+        fb->d_rms_sum = sum; fb->d_lag_state = lag_state; fb->d_lag_par = lag_par; fb->d_xhist = xhist; fb->d_rms_ring = ring;
         HG_CUDA(cudaMemsetAsync(fb->d_rms_sum, 0, S * N * es, st));
         if (fb->env_mode == 2) {
-            const size_t H = (size_t)width + 4;
-            if ((ce = cudaMalloc(&fb->d_lag_state, 3 * S * N * es)) != cudaSuccess ||
-                (ce = cudaMalloc(&fb->d_lag_par, 7 * N * es)) != cudaSuccess ||
-                (ce = cudaMalloc(&fb->d_xhist, S * H * es)) != cudaSuccess)
-                return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: replica state: %s", cudaGetErrorString(ce));
             HG_CUDA(cudaMemcpyAsync(fb->d_lag_state, fb->d_state, 3 * S * N * es, cudaMemcpyDeviceToDevice, st));
             HG_CUDA(cudaMemsetAsync(fb->d_xhist, 0, S * H * es, st));
             // the two input samples before the followers start: x[t-1], x[t-2] of every stream
@@ -324,9 +373,7 @@ hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_
             HG_CUDA(cudaMemcpy2DAsync((char*)fb->d_xhist + (H - 1) * es, H * es, xh, 2 * es, es, S, cudaMemcpyDeviceToDevice, st));
             HG_CUDA(cudaMemcpy2DAsync((char*)fb->d_xhist + (H - 2) * es, H * es, xh + es, 2 * es, es, S, cudaMemcpyDeviceToDevice, st));
         } else {
-            if ((ce = cudaMalloc(&fb->d_rms_ring, S * (size_t)width * ((N + 31) / 32 * 32) * es)) != cudaSuccess)
-                return hg::fail(HG_ERR_NOMEM, "hg_fb_process_env: follower ring (%zu bytes): %s", S * (size_t)width * N * es, cudaGetErrorString(ce));
-            HG_CUDA(cudaMemsetAsync(fb->d_rms_ring, 0, S * (size_t)width * ((N + 31) / 32 * 32) * es, st));
+            HG_CUDA(cudaMemsetAsync(fb->d_rms_ring, 0, ring_bytes, st));
         }
         fb->rms_width = width;
         fb->rms_ticks = 0;
@@ -413,6 +460,16 @@ hg_status hg_fb_process_tv(hg_fb* fb, const void* in, void* out_sum, size_t L, c
     return HG_OK;
 }
 
+hg_status hg_fb_reset_followers(hg_fb* fb) {
+    if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_reset_followers: null handle");
+    HG_CUDA(cudaSetDevice(fb->device));
+    HG_CUDA(cudaDeviceSynchronize());
+    cudaFree(fb->d_rms_sum); cudaFree(fb->d_rms_ring); cudaFree(fb->d_lag_state); cudaFree(fb->d_lag_par); cudaFree(fb->d_xhist);
+    fb->d_rms_sum = fb->d_rms_ring = fb->d_lag_state = fb->d_lag_par = fb->d_xhist = nullptr;
+    fb->rms_width = 0; fb->rms_ticks = 0; fb->lag_live = false; fb->lag_pending.clear();
+    return HG_OK;
+}
+
 hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode) {
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: null handle");
     if (mode != HG_ENV_RING && mode != HG_ENV_REPLICA) return hg::fail(HG_ERR_INVALID, "hg_fb_set_follower_mode: bad mode %d", mode);
@@ -436,14 +493,15 @@ hg_status hg_fb_get_state(hg_fb* fb, void* y1, void* y2, void* p, void* g, void*
 
 hg_status hg_fb_set_state(hg_fb* fb, const void* y1, const void* y2, const void* p, const void* g, const void* xhist) {
     if (!fb) return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: null handle");
-    if (fb->env_mode == HG_ENV_REPLICA && fb->d_rms_sum)
-        return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: replica followers are running (their lagged copies would no longer match the filters)");
+    if (fb->d_rms_sum)
+        return hg::fail(HG_ERR_INVALID, "hg_fb_set_state: envelope followers are running (their window / lagged copies would no longer match the filters); hg_fb_reset_followers first");
     HG_CUDA(cudaSetDevice(fb->device));
     HG_CUDA(cudaDeviceSynchronize());
     const size_t es = hg::dtype_size(fb->dtype), SN = (size_t)fb->S * fb->N * es;
     const void* src[4] = {y1, y2, p, g};
     for (int k = 0; k < 4; k++)
         if (src[k]) HG_CUDA(cudaMemcpy((char*)fb->d_state + k * SN, src[k], SN, cudaMemcpyHostToDevice));
+    if ((p || g) && fb->S > 1) fb->smoothers_custom = true;
     if (xhist) HG_CUDA(cudaMemcpy((char*)fb->d_xh + (size_t)fb->xh_cur * 2 * fb->S * es, xhist, 2 * fb->S * es, cudaMemcpyHostToDevice));
     return HG_OK;
 }

@@ -38,7 +38,11 @@ struct hg_fb {
     int force_F = 0;      // HG_FB_FORCE_F: 1,2,4,8 = filters per thread of the lane kernel; -1 = warp-specialised kernel
     int force_chunks = 0;
     // order-faithful mixdown (chain.cuh): link rings and credits, the virtual sample position, the CTA ticket counter
+    bool smoothers_custom = false;         // hg_fb_set_state gave the streams their own p / g (the scan's prepass reads stream 0)
     int sum_mode = 1;                      // HG_SUM_ORDERED (1, default) or HG_SUM_TREE (0)
+    hg::Epilogue epi = {0, 0.0, 0.0};      // hg_fb_set_epilogue
+    const void* cur_dry_in = nullptr;      // device pointer of the block's dry signal (hg_fb_process_voice), null: the input
+    hg::DevBuf dry_stage;
     void* d_chain_ring = nullptr;          // [links][ring samples] LL words
     size_t chain_ring_words = 0;
     int chain_ring_log2 = 0;
@@ -65,7 +69,7 @@ struct hg_fb {
     void* cur_env_out = nullptr; // device pointer of the block's envelope output, may be null
     int cur_hop = 0;
     size_t cur_env_rows = 0;
-    int env_mode = 1;            // HG_ENV_RING (1) or HG_ENV_REPLICA (2), fixed once the followers have started
+    int env_mode = 2;            // HG_ENV_REPLICA (2, default: FMA-bound, 2.3x faster on B200) or HG_ENV_RING (1); fixed once the followers have started
     void* d_lag_state = nullptr; // replica followers: [3][S][N] y1, y2, p of the lagged copies
     void* d_xhist = nullptr;     // replica followers: [S][width + 4] input samples before the current block
     void* d_lag_par = nullptr;   // replica followers: [7][N] parameters the replicas currently run with
@@ -98,6 +102,8 @@ template <typename T> struct FbK1Params {
     int dist;      // HG_DIST_*: per-band nonlinearity before the sum (lane kernel only)
     int taps;      // 0 general; 1: b1 == 0 everywhere; 2: b1 == 0 and b2 == -b0 everywhere
     chain::Params chain;      // how the bank sum travels from CTA to CTA (chain.cuh)
+    Epilogue epi;             // post-processing of out[t] at the chain's tail (kind 0: none)
+    const T* dry_in;          // [S][L] (stride in_stride): the dry signal of the epilogue (the block's input unless the caller gave another)
     long long* prof;          // debug (HG_FB_PROF): per-CTA cycle counters of the S / R roles, or null
     const T* carry_in;        // [S] rows (stride carry_stride): the running sum the chain's head starts from; null = 0
     long carry_stride;

@@ -789,7 +789,10 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                         T a1v[1] = {(T)a};
                         pout.send(C, tg + lane, a1v);
                     } else if (out_row) {
-                        if (lane < tn) out_row[tg + lane] = (T)a;
+                        if (lane < tn) {
+                            if (P.epi.kind && ordered) a = (float)epilogue_dev<T>(P.epi, (T)a, P.dry_in[(size_t)s * P.in_stride + tg + lane]);
+                            out_row[tg + lane] = (T)a;
+                        }
                     }
                     if (HG_PROF_ON(P)) pf_out += clock64() - pc0;
                 }
@@ -892,7 +895,10 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                     T a1v[1] = {acc};
                     pout.send(C, tg + lane, a1v);
                 } else if (out_row) {
-                    if (lane < tn) out_row[tg + lane] = acc;
+                    if (lane < tn) {
+                        if (P.epi.kind && ordered) acc = epilogue_dev<T>(P.epi, acc, P.dry_in[(size_t)s * P.in_stride + tg + lane]);
+                        out_row[tg + lane] = acc;
+                    }
                 }
             }
             if (HG_PROF_ON(P)) pf_out += clock64() - pc0;

@@ -412,7 +412,6 @@ hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStre
     if (!d_out) return fail(HG_ERR_INVALID, "scan mode needs out_sum");
     const int N = fb->N, S = fb->S;
     int F = (sizeof(T) == 4) ? 8 : 4;
-    if (const char* e = getenv("HG_SCAN_F")) { if (atoi(e) == 4) F = 4; if (atoi(e) == 8 && sizeof(T) == 4) F = 8; }
     // enough lanes for ~2 warps per scheduler; chunks are multiples of the input staging size
     const long want_threads = (long)fb->sm_count * 4 * 32 * 2;
     long C = (want_threads * F + (long)S * N - 1) / ((long)S * N);

@@ -93,6 +93,22 @@ template <typename T> __device__ __noinline__ T softclip_dev(T v) {
     return (T)(sign * width + (1 - width) * 2.0 / PI_REF * atan(PI_REF * gap / (2 * (1 - width))));
 }
 
+// Post-processing of the finished bank sum, fused into the store of out[t] (the caller loops' last step):
+//   HG_EPI_SOFTCLIP  out = softclip(dry * in + sum, width)   tests/filterbank.cpp:205-207 (the outer softclip(., 0.9))
+//   HG_EPI_LIMITER   out = 2/PI * atan(dry * in + sum)       src/wave.h:150 `limiter` (tests/harmbank.cpp:76), evaluated
+//                    directly — the reference reads it from a 4096-point interpolated table
+// evaluated in double like the reference's callers and rounded to T; device atan: tolerance-bounded, not bit-exact.
+struct Epilogue { int kind; double dry, width; };
+template <typename T> __device__ __noinline__ T epilogue_dev(const Epilogue e, T sum, T in) {
+    const double PI_REF = 3.14159265359;
+    const double v = e.dry * (double)in + (double)sum;
+    if (e.kind == 2) return (T)(2.0 / PI_REF * atan(v));
+    if (fabs(v) < e.width) return (T)v;
+    const double sign = (0.0 < v) - (v < 0.0);
+    const double gap = v - sign * e.width;
+    return (T)(sign * e.width + (1 - e.width) * 2.0 / PI_REF * atan(PI_REF * gap / (2 * (1 - e.width))));
+}
+
 // Transposed CTA reduction of one tile of per-thread partial sums.
 //   rb[t * RS + tid], RS = NT + NW  (RS == NW mod 32: the per-sample STS of all threads and the
 //   strided reads below are both bank-conflict free).  Warp w owns samples [w*SPW, (w+1)*SPW),

@@ -115,15 +115,19 @@ hg_status hg_fb_process_events(hg_fb* fb, const void* in, void* out_sum, size_t 
  * boundaries; boost and mix keep their per-sample smoothing.  n_rows * hop >= L; the bank keeps the last row. */
 hg_status hg_fb_process_tv(hg_fb* fb, const void* in, void* out_sum, size_t L, const void* rows, size_t n_rows, int hop,
                            void* cuda_stream);
-/* How the followers obtain y[t-width].  HG_ENV_RING (default): a ring of the last `width` squares per filter
+/* How the followers obtain y[t-width].  HG_ENV_RING: a ring of the last `width` squares per filter
  * in device memory (8 bytes of HBM traffic per filter-sample, width*sizeof(T) bytes per filter).
- * HG_ENV_REPLICA: a second copy of every filter runs `width` ticks behind on the same input and regenerates
+ * HG_ENV_REPLICA (default): a second copy of every filter runs `width` ticks behind on the same input and regenerates
  * y[t-width] bit for bit (no ring, twice the arithmetic, ~2x faster on B200).  Parameter changes reach the
  * replicas `width` ticks after the filters (the library keeps the pending sets and splits blocks at the
  * hand-over ticks); the one restriction is that every tick must then be rendered through hg_fb_process_env
  * (plain hg_fb_process is refused while replica followers run).  Call before the first hg_fb_process_env. */
 enum { HG_ENV_RING = 1, HG_ENV_REPLICA = 2 };
 hg_status hg_fb_set_follower_mode(hg_fb* fb, int mode);
+/* Drop the followers (running sums, ring or replicas): the next hg_fb_process_env starts them afresh, like a newly
+ * constructed RMSbank.  While followers run, plain hg_fb_process / hg_fb_set_state are refused in BOTH modes — the
+ * followers must see every tick, and their state is not part of hg_fb_get_state. */
+hg_status hg_fb_reset_followers(hg_fb* fb);
 hg_status hg_fb_process_env(hg_fb* fb, const void* in, void* out_sum, void* out_env, size_t L, int width,
                             int hop, void* cuda_stream);
 /* state access (streaming / checkpoint tests): y1,y2,p,g are [n_streams][n_filters]; xhist is
@@ -142,6 +146,19 @@ hg_status hg_fb_last_launch(hg_fb* fb, int* mode_used, int* launches, int* filte
  *   per-filter values, different summation order (float: ~3e-5 of peak at 4096 filters, 3e-4 at 65 536). */
 enum { HG_SUM_TREE = 0, HG_SUM_ORDERED = 1 };
 hg_status hg_fb_set_sum_mode(hg_fb* fb, int mode);
+/* new: post-processing of the finished bank sum, fused into the store of out_sum[t] (kernel epilogue) — the last
+ * step of the reference's caller loops:
+ *   HG_EPI_SOFTCLIP  out = softclip(dry * in[t] + sum[t], width)   tests/filterbank.cpp:205-207 (outer softclip(., 0.9))
+ *   HG_EPI_LIMITER   out = 2/PI * atan(dry * in[t] + sum[t])       src/wave.h:150 `limiter`, tests/harmbank.cpp:76
+ * evaluated in double and rounded to T (device atan: within tolerance of libm, not bit-identical).  HG_EPI_NONE
+ * restores the plain sum.  In a sharded render the rank that holds the chain's tail applies it. */
+enum { HG_EPI_NONE = 0, HG_EPI_SOFTCLIP = 1, HG_EPI_LIMITER = 2 };
+hg_status hg_fb_set_epilogue(hg_fb* fb, int kind, double dry, double width);
+/* Block form of the tests/filterbank.cpp:200-215 process body: out[t] = epilogue(dry * dry_in[t] + F(in[t], distortion))
+ * with the epilogue set by hg_fb_set_epilogue — `in` is the (pre-clipped, driven) signal the bank filters, `dry_in`
+ * the raw input of the dry path (NULL: the same block).  Exact mode. */
+hg_status hg_fb_process_voice(hg_fb* fb, const void* in, const void* dry_in, void* out_sum, size_t L, int distortion,
+                              void* cuda_stream);
 /* Synchronous health check (copies one flag from the device): HG_ERR_CUDA if the ordered mixdown's watchdog fired
  * during an earlier asynchronous block.  Host-pointer blocks check this before returning. */
 hg_status hg_fb_check(hg_fb* fb);

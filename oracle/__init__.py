@@ -51,6 +51,7 @@ def lib():
             f("hgo_fb_process").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
             f("hgo_fb_process_from").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
             f("hgo_fb_get_smoothed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            f("hgo_epilogue").argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_double, C.c_double]
             f("hgo_osc_create").restype = C.c_void_p
             f("hgo_osc_create").argtypes = [C.c_int, C.c_int]
             f("hgo_osc_destroy").argtypes = [C.c_void_p]
@@ -156,6 +157,18 @@ class Filterbank(_Base):
         g = np.empty(self.N, self.dtype)
         self._f("hgo_fb_get_smoothed")(self._h, _ptr(p), _ptr(g))
         return p, g
+
+
+def epilogue(kind, x, s=None, dry=0.0, width=0.9):
+    """The caller loops' post-processing per sample, in double like the reference: "softclip" ->
+    softclip(dry*x + s, width) (tests/filterbank.cpp:205-207), "limiter" -> limiter(dry*x + s) (src/wave.h:150),
+    "preclip" -> softclip(x, width).  x, s: arrays of one dtype; returns that dtype."""
+    x = np.ascontiguousarray(x)
+    s = None if s is None else np.ascontiguousarray(s, dtype=x.dtype)
+    out = np.empty_like(x)
+    k = {"softclip": 1, "limiter": 2, "preclip": 3}[kind]
+    lib().hgo_epilogue_strict(k, DTYPES[np.dtype(x.dtype)], _ptr(x), _ptr(s), _ptr(out), len(x), float(dry), float(width))
+    return out
 
 
 def chained_sum(banks, x, block=4096, distortion=0):
