@@ -53,6 +53,8 @@ SYMBOLS = [
     ("hg_comm_init_rank", _i, [C.POINTER(_vp), _i, _i, _vp, _i]),
     ("hg_comm_init_all", _i, [C.POINTER(_vp), _i, _pi]),
     ("hg_comm_destroy", _i, [_vp]),
+    ("hg_comm_group_start", _i, []),
+    ("hg_comm_group_end", _i, []),
     ("hg_comm_rank", _i, [_vp]),
     ("hg_comm_size", _i, [_vp]),
     ("hg_fb_process_sharded", _i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),

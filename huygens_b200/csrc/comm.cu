@@ -217,6 +217,17 @@ hg_status hg_comm_destroy(hg_comm* c) {
     return HG_OK;
 }
 
+hg_status hg_comm_group_start(void) {
+    if (!nccl()) return hg::fail(HG_ERR_NCCL, "hg_comm_group_start: libnccl.so.2 could not be loaded");
+    HG_NCCL(nccl()->GroupStart());
+    return HG_OK;
+}
+hg_status hg_comm_group_end(void) {
+    if (!nccl()) return hg::fail(HG_ERR_NCCL, "hg_comm_group_end: libnccl.so.2 could not be loaded");
+    HG_NCCL(nccl()->GroupEnd());
+    return HG_OK;
+}
+
 int hg_comm_rank(const hg_comm* c) { return c ? c->rank : -1; }
 int hg_comm_size(const hg_comm* c) { return c ? c->size : 0; }
 

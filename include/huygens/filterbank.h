@@ -21,6 +21,8 @@ public:
 
     // reference: src/filterbank.h:36
     Filterbank(int order, int N = 1, double k_p = 0.1, double k_g = 1) { init(order, N, k_p, k_g, 0, 1); }
+    // new: the same bank on CUDA device `device` (one shard of a filter-partitioned bank lives on each GPU)
+    Filterbank(int order, int N, double k_p, double k_g, int device) { init(order, N, k_p, k_g, 0, 1, device); }
 
     // new: N resonant band-passes {g,0,-g} / {-2Q cos w, Q^2} at `frequencies` (Hz), pole radius Q
     // ("Q" is the pole radius throughout the reference, src/filter.h:123-138), unity gain at the
@@ -103,13 +105,28 @@ public:
     void process_env(const T* in, T* out_sum, T* env, size_t L, int width = SR / 20, int hop = 64, void* cuda_stream = nullptr) {
         hg_check(hg_fb_process_env(fb, in, out_sum, env, L, width, hop, cuda_stream));
     }
+    // new: collective render of a filter-partitioned bank — this object holds rank hg_comm_rank(comm)'s consecutive
+    // slice of the filters, every rank passes the same block; HG_SHARD_CHAIN keeps operator()'s index-order sum across
+    // the GPUs (bit-identical to one bank, result on the last rank unless `root` says otherwise)
+    void process_sharded(hg_comm* comm, const T* in, T* out_sum, size_t L, int shard_mode = HG_SHARD_CHAIN, int root = -1, void* cuda_stream = nullptr) {
+        hg_check(hg_fb_process_sharded(fb, comm, in, out_sum, L, shard_mode, root, cuda_stream));
+    }
+    // new: post-processing fused into the store of the bank sum — the last step of the reference's caller loops:
+    // HG_EPI_SOFTCLIP: softclip(dry * in + sum, width) (tests/filterbank.cpp:205-207); HG_EPI_LIMITER (src/wave.h:150)
+    void epilogue(int kind, double dry = 0, double width = 0.9) { hg_check(hg_fb_set_epilogue(fb, kind, dry, width)); }
+    // new: out[t] = epilogue(dry * dry_in[t] + bank(in[t], softclip per band)) — tests/filterbank.cpp:200-215 as a block
+    void process_voice(const T* in, const T* dry_in, T* out_sum, size_t L, int distortion = HG_DIST_SOFTCLIP, void* cuda_stream = nullptr) {
+        hg_check(hg_fb_process_voice(fb, in, dry_in, out_sum, L, distortion, cuda_stream));
+    }
+    // HG_SUM_ORDERED (default): the mixdown in the reference's index order, bit-identical; HG_SUM_TREE: per-CTA partial sums
+    void sum_mode(int mode) { hg_check(hg_fb_set_sum_mode(fb, mode)); }
     int size() const { return N; }
     hg_fb* handle() { return fb; }
 
 protected:
-    void init(int order_, int N_, double k_p, double k_g, int flags, int streams) {
+    void init(int order_, int N_, double k_p, double k_g, int flags, int streams, int device = 0) {
         order = order_; N = N_;
-        hg_check(hg_fb_create(&fb, hg_dtype<T>::value, HUYGENS_ARITH, order, N, streams, k_p, k_g, flags, 0));
+        hg_check(hg_fb_create(&fb, hg_dtype<T>::value, HUYGENS_ARITH, order, N, streams, k_p, k_g, flags, device));
         forwards.assign((size_t)N * (order + 1), 0);
         backs.assign((size_t)N * std::max(order, 1), 0);
         last_bands.assign((size_t)N, 0);

@@ -178,6 +178,12 @@ hg_status hg_comm_get_unique_id(void* id128);
 hg_status hg_comm_init_rank(hg_comm** out, int n_ranks, int rank, const void* id128, int device);
 hg_status hg_comm_init_all(hg_comm** comms, int n_devices, const int* devices /* NULL: 0..n-1 */);
 hg_status hg_comm_destroy(hg_comm* comm);
+/* ncclGroupStart / ncclGroupEnd: when ONE host thread issues the collective call of several ranks
+ * (hg_comm_init_all), bracket the ranks' hg_fb_process_sharded calls with these (required for HG_SHARD_REDUCE and
+ * for a `root` other than the chain's tail; harmless otherwise).  Use device buffers there: a host-buffer call
+ * blocks until its own kernel has finished, which needs the other ranks' kernels to be running. */
+hg_status hg_comm_group_start(void);
+hg_status hg_comm_group_end(void);
 int hg_comm_rank(const hg_comm* comm);
 int hg_comm_size(const hg_comm* comm);
 /* HG_SHARD_CHAIN: operator()'s index-order sum (src/filterbank.h:130) is kept across the devices — the running

@@ -145,3 +145,27 @@ def test_dropin_per_sample_banks(harness, oracle_lib):
         assert abs(got[t, 4] - y[0]) <= 1e-12 * max(1.0, abs(y[0]))
         clipped = np.clip(bands[:, 0] * g, -0.125, 0.125).sum()
         assert abs(got[t, 5] - clipped) <= 1e-12 * max(1.0, abs(clipped))
+
+
+def test_sharded_demo_single_process_all_gpus(harness, tmp_path, oracle_lib):
+    """harness/sharded_demo: one C++ host process, hg_comm_init_all, one soundmath::Filterbank shard per GPU, the
+    running bank-sum row handed GPU to GPU (every GPU of the box; a one-GPU box runs the same code with one rank).
+    The first block must be the oracle's single-bank sum, bit for bit."""
+    import torch
+    from conftest import oracle_chained
+    G = max(1, min(torch.cuda.device_count(), 4))
+    N, seconds = 600 * G + 7, 0.25
+    out = tmp_path / "sum.f32"
+    r = subprocess.run([os.path.join(harness, "sharded_demo"), "--filters", str(N), "--seconds", str(seconds), "--gpus", str(G),
+                        "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    L = int(seconds * 48000)
+    assert info["gpus"] == G and info["frames"] == L and info["exchange"] == "chain"
+    got = np.fromfile(out, dtype=np.float32)
+    ref = oracle_chained(N, np.float32, design.chirp(L, dtype=np.float32))
+    assert np.array_equal(got, ref)
+    r = subprocess.run([os.path.join(harness, "sharded_demo"), "--filters", str(N), "--seconds", str(seconds), "--gpus", str(G),
+                        "--reduce", "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert rel_err(np.fromfile(out, dtype=np.float32), ref) <= 1e-5
