@@ -32,7 +32,8 @@ SR = 48000
 SLOTS_PER_FILTER_SAMPLE = 11        # 11 mul + 7 add, every add fusable: SURVEY.md §8(d)
 WORKLOADS = {
     # BASELINE configs[0]: Filterbank<double>, 64 resonant band-passes (resynthesis recipe), 10 s white noise
-    "c1": dict(N=64, seconds=10, f_lo=369.0, f_hi=23630.0, r=0.999, k_p=0.1, k_g=1.0, input="white", dtype="f64"),
+    # (f_i = 0.5 (i+1) SR / (N+1), R = 0.999, gains 1/|H| in the taps {g,0,-g}, boost(1) + open(), k_p = 0.1, k_g = 1)
+    "c1": dict(N=64, seconds=10, recipe="resynthesis", r=0.999, k_p=0.1, k_g=1.0, input="white", dtype="f64", f_lo=0.0, f_hi=0.0),
     # name: (filters per GPU, seconds, f_lo, f_hi, r, k_p, k_g, input)
     "c2": dict(N=4096, seconds=60, f_lo=27.5, f_hi=20000.0, r=0.999, k_p=0.001, k_g=1.0, input="chirp"),
     # BASELINE configs[2] (65,536 filters; a parity/scaling case, not the headline): 10 s blocks
@@ -65,6 +66,7 @@ def parse():
     ap.add_argument("--sum", default="ordered", choices=["ordered", "tree"], help="mixdown: ordered = the reference's index order and rounding (bit-identical, default); tree = per-CTA partial sums (tolerance mode)")
     ap.add_argument("--exchange", default="chain", choices=["chain", "reduce"], help="N > 1, filter-partitioned: chain = the running bank-sum row crosses the GPUs in filter order (bit-identical to one bank); reduce = ncclReduce of order-free partial sums")
     ap.add_argument("--parity-samples", type=int, default=48000, help="prefix of the block checked against the oracle's own sequential sum (0: skip)")
+    ap.add_argument("--no-side", action="store_true", help="N = 1: skip the side measurements of the other BASELINE configurations")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the configs[2] strong-scaling block")
     ap.add_argument("--env", action="store_true", help="fuse per-band RMSbank envelope followers (width 2400, hop 64) behind the filters")
     return ap.parse_args()
@@ -76,6 +78,9 @@ def bank_params(w, rank, world):
     if w.get("streams", 1) > 1:                            # stream-partitioned: the same bank on every GPU, no exchange
         rank, world = 0, 1
     lo, hi = filter_range(w["N"] * world, rank, world)     # rank's slice of an N*world bank (N filters per GPU)
+    if w.get("recipe") == "resynthesis":                   # tests/resynthesis.cpp:48-54: gains in the taps, mix = open()
+        _, fwd, back = design.resynthesis_bank(w["N"] * world, w["r"])
+        return fwd[lo:hi], back[lo:hi], np.ones(hi - lo)
     freqs = design.log_spaced(w["N"] * world, w["f_lo"], w["f_hi"])[lo:hi]
     return design.resonator_bank(freqs, w["r"])
 
@@ -184,9 +189,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(w, dtype, n_samples, threads):
+def cpu_baseline(w, dtype, n_samples, threads, native=False):
     """Oracle strict tick loop over the head of the same input; `threads` bank partitions in parallel
-    (the reference itself is single-threaded; partitioning filters is what a host could do)."""
+    (the reference itself is single-threaded; partitioning filters is what a host could do).
+    native: the same source built with -march=native on this host (BASELINE.md §2's second figure)."""
     import oracle
     oracle.build()
     N = w["N"]
@@ -195,7 +201,7 @@ def cpu_baseline(w, dtype, n_samples, threads):
     parts = np.array_split(np.arange(N), threads)
     banks = []
     for idx in parts:
-        fb = oracle.Filterbank(2, len(idx), w["k_p"], w["k_g"], dtype=dtype, mode="strict")
+        fb = oracle.Filterbank(2, len(idx), w["k_p"], w["k_g"], dtype=dtype, mode="strict", native=native)
         for j, n in enumerate(idx):
             fb.coefficients(j, fwd[n], back[n])
         fb.mix(gains[idx])
@@ -224,9 +230,14 @@ def run_reference(args, w, rank, world):
     timing it would flatter the GPU arm.  Its throughput is reported next to the port for transparency."""
     if rank != 0:
         return
-    dtype = np.float32
+    dtype = np.float64 if w.get("dtype") == "f64" else np.float32
     threads = os.cpu_count() or 1
-    n_samples = 2 * SR                       # bounded sample per step: 2 s of the 60 s block
+    if w.get("streams", 1) == 1 and world > 1:
+        # the whole job's bank: the GPU arm at N GPUs renders N x filters_per_gpu filters (weak scaling), so does this arm
+        w = dict(w, N=w["N"] * world)
+    n_samples = 2 * SR                       # bounded sample per step: 2 s of the block
+    while w["N"] * n_samples > 8e9 and n_samples > 4800:
+        n_samples //= 2
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(w, dtype, n_samples // 4, threads)
     times = []
@@ -235,7 +246,8 @@ def run_reference(args, w, rank, world):
         times.append(dt)
     T = float(np.mean(times))
     val = w["N"] * n_samples / T
-    sample = f"{w['N']} filters x first {n_samples} samples of the 60 s chirp per step, {threads} threads over filter partitions"
+    sample = (f"{w['N']} filters (the whole {world}-GPU job's bank) x first {n_samples} samples of the {w['seconds']} s {w['input']} per step, "
+              f"{threads} threads over filter partitions")
     ref_shim = None
     try:
         import oracle
@@ -258,8 +270,8 @@ def run_reference(args, w, rank, world):
     line = {
         "impl": "reference", "metric": "filter-samples/s (biquad bank)", "value": val, "unit": "filter-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(w, args, world),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.get("dtype", "f32"), "data": "synthetic",
+        "config": dict(workload_config(dict(w, N=w["N"] // (world if w.get("streams", 1) == 1 else 1)), args, world), filters_timed=w["N"], samples_timed_per_step=n_samples),
         "cpu_baseline": {"value": val, "unit": "filter-samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "filter-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -436,11 +448,83 @@ def strong_c3(args, rank, world, local, comm, flush):
     return res
 
 
+def side_measurements(args, local, flush, peak):
+    """The other BASELINE configurations on this GPU, timed in the same run so that the driver's record carries them
+    (each a few short launches): configs[2] on one GPU, configs[3] with and without the fused followers, the Oscbank
+    and RMSbank kernels alone.  Device-resident inputs, CUDA events, L2 flushed between launches."""
+    import torch
+    import huygens_b200 as hb
+    from huygens_b200 import design
+
+    def timed(fn, reps=3):
+        fn()
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(reps):
+            flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return float(np.mean(ts))
+
+    res = {}
+    slots = peak["slots_per_s"]
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm = 6650.0
+    for name in ("c3", "c4"):
+        w = dict(WORKLOADS[name])
+        L, S = int(w["seconds"] * SR), w.get("streams", 1)
+        fb = make_bank(hb.Filterbank, w, 0, 1, np.float32, arith=args.arith, device=local)
+        x = torch.from_numpy(synth_input(w, L, np.float32)).cuda()
+        out = torch.empty_like(x)
+        t = timed(lambda: fb.process(x, out=out))
+        fs = float(w["N"]) * S * L / t
+        res[name] = {"workload": workload_config(w, args, 1)["workload"], "ms_per_block": t * 1e3, "value": fs, "unit": "filter-samples/s",
+                     "roofline_frac": fs * SLOTS_PER_FILTER_SAMPLE / slots, "kernel": {0: "K1-ws", -2: "K1-ru"}.get(fb.last_launch()["filters_per_thread"], "lanes")}
+        if name == "c4":
+            env = torch.empty((S, L // 64, w["N"]), dtype=torch.float32, device="cuda")
+            fbe = make_bank(hb.Filterbank, w, 0, 1, np.float32, arith=args.arith, device=local)
+            t = timed(lambda: fbe.process_env(x, width=2400, hop=64, out=out, env=env))
+            fs = float(w["N"]) * S * L / t
+            res["c4_followers"] = {"workload": "the same + one RMSbank(2400) follower per (stream, band), envelopes every 64 samples (replica followers)",
+                                   "ms_per_block": t * 1e3, "value": fs, "unit": "filter-samples/s", "roofline_frac": fs * (SLOTS_PER_FILTER_SAMPLE + 3) / slots,
+                                   "slots_per_unit": SLOTS_PER_FILTER_SAMPLE + 3}
+            del fbe, env
+        del fb, x, out
+    N, Lo = 65536, 480000
+    osc = hb.Oscbank(N, dtype=np.float32, arith=args.arith, device=local)
+    osc.set_frequencies(design.log_spaced(N, 20.0, 20000.0))
+    osc.open()
+    amps = torch.full((N,), 1.0 / N, dtype=torch.float32, device="cuda")
+    t = timed(lambda: osc.process(Lo, amps=amps, want_mix=True, device_out=True))
+    ps = float(N) * Lo / t
+    res["oscbank"] = {"workload": f"Oscbank<float> {N} partials x {Lo} ticks, mixdown() + amplitude-weighted mix per tick (index-order sums)",
+                      "ms_per_block": t * 1e3, "value": ps, "unit": "partial-samples/s", "roofline_frac": ps * 11 / slots,
+                      "slots_per_unit": "9 FP32 slots + 2 IEEE divisions counted as 1 each (SURVEY.md 8d)"}
+    del osc
+    C_, Lr = 65536, 96000
+    z = torch.rand((C_, Lr), dtype=torch.float32, device="cuda")
+    rms = hb.RMSbank(C_, 2400, dtype=np.float32, device=local)
+    t = timed(lambda: rms.process(z))
+    res["rmsbank"] = {"workload": f"RMSbank<float> {C_} channels x {Lr} ticks, width 2400", "ms_per_block": t * 1e3,
+                      "value": float(C_) * Lr / t, "unit": "channel-samples/s", "hbm_GBps_algorithmic": C_ * Lr * 8 / t / 1e9,
+                      "roofline_frac_hbm": C_ * Lr * 8 / t / 1e9 / hbm}
+    return res
+
+
 def workload_config(w, args, world):
     tname = "double" if w.get("dtype") == "f64" else "float"
     sname = f"{w['streams']} streams x " if w.get("streams", 1) > 1 else ""
-    return {"workload": f"Filterbank<{tname}> {sname}{w['N']} log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, "
-                        f"fwd {{1,0,-1}}, k_p={w['k_p']}, k_g={w['k_g']}), {w['seconds']} s 48 kHz {w['input']}, summed output",
+    bank = (f"resonant biquads/GPU of the resynthesis recipe (f_i = 0.5 (i+1) SR/(N+1), R={w['r']}, gains in the taps, boost(1) + open(), "
+            if w.get("recipe") == "resynthesis" else
+            f"log-spaced resonant biquads/GPU ({w['f_lo']} Hz-{w['f_hi']} Hz, r={w['r']}, fwd {{1,0,-1}}, ")
+    return {"workload": f"Filterbank<{tname}> {sname}{w['N']} {bank}k_p={w['k_p']}, k_g={w['k_g']}), {w['seconds']} s 48 kHz {w['input']}, summed output",
             "filters_per_gpu": w["N"], "filters_total": w["N"] * (1 if w.get("streams", 1) > 1 else world),
             "streams_total": w.get("streams", 1) * (world if w.get("streams", 1) > 1 else 1), "samples": int(w["seconds"] * SR),
             "partition": ("streams" if w.get("streams", 1) > 1 else "filters") if world > 1 else "none", "mode": args.mode, "arith": args.arith,
@@ -620,10 +704,10 @@ def main():
     value = units / t_total
     per_gpu_kernel = float(N) * S * L * args.steps / t_kernel
     achieved = per_gpu_kernel * SLOTS_PER_FILTER_SAMPLE
-    nominal = peak["sm_count"] * 128 * 1.965e9
+    nominal = peak["sm_count"] * (64 if w.get("dtype") == "f64" else 128) * 1.965e9
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if args.mode == "exact" and args.workload == "c2":
             traffic = {"dram_bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "samples_per_launch": tr["samples_per_launch"],
                        "algorithmic_bytes_per_launch": 8 * tr["samples_per_launch"], "source": tr["source"], "note": tr["note"]}
@@ -638,9 +722,9 @@ def main():
         "e2e": {"value": units / t_e2e, "unit": "filter-samples/s", "h2d_bytes_per_step": int(S * L * x_host.element_size()), "d2h_bytes_per_step": int(S * L * x_host.element_size() + (env_h.nbytes if args.env else 0))},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
+        "roofline": {"bound": "fp64_fma" if w.get("dtype") == "f64" else "fp32_fma", "achieved": achieved / 1e12, "peak": peak["slots_per_s"] / 1e12, "unit": "Tslot/s",
                      "frac": achieved / peak["slots_per_s"], "traffic": traffic,
-                     "peak_source": "hg_fma_peak FFMA microbenchmark, measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                     "peak_source": "hg_fma_peak FFMA / DFMA microbenchmark, measured in this run (MEASURED_PEAKS.json has no FP32 / FP64 figure)",
                      "frac_of_nominal": achieved / nominal, "slots_per_unit": SLOTS_PER_FILTER_SAMPLE,
                      "kernel_ms": t_kernel / args.steps * 1e3,
                      # bit-exact ceiling: every lane must run the FMUL->FADD->FADD chain once per sample, serially
@@ -670,6 +754,11 @@ def main():
                                  "note": "Filterbank + per-band RMSbank(2400) followers; y[t-2400] regenerated by lagged replica filters (no ring); envelopes every 64 samples"})
     if parity:
         line["parity"] = parity
+    if world == 1 and args.workload == "c2" and not args.no_side and args.mode == "exact" and not args.env:
+        try:
+            line["side"] = side_measurements(args, local, flush, peak)
+        except Exception as e:
+            line["side"] = {"failed": str(e).splitlines()[0][:300]}
     if strong:
         line["strong_c3"] = strong
     if exchange:
@@ -678,10 +767,16 @@ def main():
     if scan_info:
         line["scan"] = scan_info
     if not args.no_cpu_baseline:
-        n_s = 3 * SR
+        n_s = 3 * SR if N * 3 * SR <= 4e9 else max(2400, int(4e9 / N) // 2400 * 2400)
         v, dt = cpu_baseline(w, dtype, n_s, 1)
         line["cpu_baseline"] = {"value": v, "unit": "filter-samples/s", "cores": 1, "kind": "port",
-                                "sample": f"{N} filters x first {n_s} samples of the same chirp, strict oracle, {dt:.1f} s"}
+                                "sample": f"{N} filters x first {n_s} samples of the same input, strict oracle built like tests/build.sh:8 (g++ -O3, no -march), {dt:.1f} s"}
+        try:
+            v2, dt2 = cpu_baseline(w, dtype, n_s, 1, native=True)
+            line["cpu_baseline"]["march_native"] = {"value": v2, "unit": "filter-samples/s", "cores": 1,
+                                                    "sample": f"same loop and sample, g++ -O3 -march=native -ffp-contract=off on this host, {dt2:.1f} s"}
+        except Exception as e:          # the second figure is informative only
+            line["cpu_baseline"]["march_native"] = {"unavailable": str(e).splitlines()[0][:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -81,6 +81,27 @@ def lib():
     return _LIB
 
 
+_LIB_NATIVE = None
+
+
+def lib_native():
+    """liboracle_native.so: the strict restatement built with -march=native ON THIS HOST (make -C oracle native);
+    only the Filterbank entry points are bound.  Used by bench.py's cpu_baseline for the second, fairer figure."""
+    global _LIB_NATIVE
+    if _LIB_NATIVE is None:
+        out = subprocess.run(["make", "-B", "-C", _HERE, "native"], capture_output=True, text=True)   # always rebuilt: -march=native of another machine must never be loaded
+        if out.returncode != 0:
+            raise RuntimeError("oracle -march=native build failed:\n" + out.stdout + out.stderr)
+        L = C.CDLL(os.path.join(_HERE, "liboracle_native.so"))
+        ref = lib()
+        for name in ("hgo_fb_create", "hgo_fb_destroy", "hgo_fb_coefficients", "hgo_fb_boost", "hgo_fb_mix", "hgo_fb_open",
+                     "hgo_fb_process", "hgo_fb_process_from", "hgo_fb_get_smoothed"):
+            f, g = getattr(L, name + "_strict"), getattr(ref, name + "_strict")
+            f.restype, f.argtypes = g.restype, g.argtypes
+        _LIB_NATIVE = L
+    return _LIB_NATIVE
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -92,8 +113,10 @@ class _Base:
         self.mode = mode
         self._h = None
 
+    native = False      # Filterbank(native=True): the -march=native build of the strict restatement (timing only)
+
     def _f(self, name):
-        return getattr(lib(), f"{name}_{self.mode}")
+        return getattr(lib_native() if self.native else lib(), f"{name}_{self.mode}")
 
     def _arr(self, v):
         return np.ascontiguousarray(np.asarray(v, dtype=np.float64).astype(self.dtype))
@@ -102,8 +125,10 @@ class _Base:
 class Filterbank(_Base):
     """Filterbank<T>(order, N, k_p, k_g) — filterbank.h:36; fixed=True -> FFilterbank<T,N,order>(k_p,k_g) :203."""
 
-    def __init__(self, order, N=1, k_p=0.1, k_g=1.0, dtype=np.float64, mode="strict", fixed=False):
+    def __init__(self, order, N=1, k_p=0.1, k_g=1.0, dtype=np.float64, mode="strict", fixed=False, native=False):
         super().__init__(dtype, mode)
+        self.native = bool(native)
+        assert not (native and mode != "strict")
         self.N, self.order = N, order
         self._h = self._f("hgo_fb_create")(DTYPES[self.dtype], int(fixed), order, N, k_p, k_g)
 
