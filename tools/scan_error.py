@@ -3,7 +3,7 @@
 exact mode (must be bit-exact per filter) and scan mode (tolerance-bounded), for the full-range bank
 and for a 500 Hz..20 kHz bank.  Test/measurement tool: uses the oracle as the checker.
 
-    python tools/scan_error.py [--seconds 60] [--out profiles/scan_error_r1.json]
+    python tools/scan_error.py [--seconds 60] [--out profiles/scan_error_r2.json]
 """
 import argparse
 import json
@@ -25,23 +25,19 @@ from conftest import rel_err, snr_db  # noqa: E402
 
 
 def oracle_sum(fwd, back, gains, x, dtype, k_p, k_g, threads):
+    """the oracle's own sequential index-order sum of the whole bank (oracle.chained_sum: consecutive filter
+    partitions on the host threads, each continuing the running row of the one before — bit-identical to one
+    oracle.Filterbank of all the filters)"""
     N = len(gains)
-    parts = np.array_split(np.arange(N), threads)
-    outs = [None] * threads
-
-    def work(i):
-        idx = parts[i]
+    banks = []
+    for idx in np.array_split(np.arange(N), min(threads, N)):
         fb = oracle.Filterbank(2, len(idx), k_p, k_g, dtype=dtype, mode="strict")
         for j, n in enumerate(idx):
             fb.coefficients(j, fwd[n], back[n])
         fb.mix(gains[idx])
         fb.boost(np.ones(len(idx)))
-        outs[i] = fb.process(x).astype(np.float64)
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    return sum(outs)
+        banks.append(fb)
+    return oracle.chained_sum(banks, x)
 
 
 def main():
@@ -64,15 +60,16 @@ def main():
             ref = oracle_sum(fwd, back, gains, x, dtype, 0.001, 1.0, threads)
             t_ref = time.time() - t0
             row = {"dtype": np.dtype(dtype).name, "filters": N, "samples": L, "f_lo": f_lo, "r": 0.999,
-                   "oracle": "strict, summed in double over %d filter partitions" % threads, "oracle_s": round(t_ref, 1),
+                   "oracle": "strict, the reference's sequential index-order sum in T (chained over %d host threads)" % threads, "oracle_s": round(t_ref, 1),
                    "peak": float(np.max(np.abs(ref)))}
-            for mode in ("exact", "scan"):
-                fb = hb.Filterbank(2, N, 0.001, 1.0, dtype=dtype)
+            for mode, summ in (("exact", "ordered"), ("exact", "tree"), ("scan", "ordered")):
+                fb = hb.Filterbank(2, N, 0.001, 1.0, dtype=dtype, sum_mode=summ)
                 fb.coefficients(0, fwd, back)
                 fb.mix(gains)
                 fb.boost(np.ones(N))
                 d = fb.process(x, mode=mode)
-                row[mode] = {"max_abs_err_rel_peak": rel_err(d, ref), "snr_db": snr_db(d, ref)}
+                key = mode if summ == "ordered" else f"{mode}_{summ}_sum"
+                row[key] = {"max_abs_err_rel_peak": rel_err(d, ref), "snr_db": snr_db(d, ref), "bit_identical": bool(np.array_equal(d, ref))}
             res.append(row)
             print(json.dumps(row), flush=True)
     if args.out:
