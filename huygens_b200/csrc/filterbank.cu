@@ -521,8 +521,9 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
             const long long now = fb->rms_ticks + (long long)t0;
             while (!fb->lag_pending.empty() && fb->lag_pending.front().tick <= now) {
                 const hg_fb::LagPending& pe = fb->lag_pending.front();
+                // pageable source: cudaMemcpyAsync returns once the set has been copied to the driver's staging
+                // buffer, so it may be dropped right away — no stream synchronisation on the render path
                 HG_CUDA(cudaMemcpyAsync(fb->d_lag_par, pe.par.data(), pe.par.size(), cudaMemcpyHostToDevice, st));
-                HG_CUDA(cudaStreamSynchronize(st));          // pageable source: let the copy land before the set is dropped
                 fb->lag_taps = pe.taps;
                 fb->lag_pending.pop_front();
             }

@@ -15,7 +15,7 @@
 //               TMA bulk copies
 //     G warp    the chain's gateway: keeps the inbound packets of the next two tiles in flight and drops the running
 //               row into shared memory for S warp 0, so no S warp ever waits on an L2 round trip
-// Tile formats.  Strict arithmetic without per-band output or followers (VF): the RU warps also own the mix gains and
+// Tile formats.  Strict arithmetic without per-band output or ring followers (VF): the RU warps also own the mix gains and
 // leave the mixdown TERMS v = fl(y*g) in the tile, sample-major [32 samples][32 filters]: an S warp fetches the 32
 // terms of its sample with 8 LDS.128 and its whole stage is the 32-deep FADD chain.  Otherwise the tile holds y,
 // filter-major, and the S warps own the gains (fused multiply-add, per-band rows, followers reading y back).
@@ -192,8 +192,8 @@ __device__ __forceinline__ void ru_tile_v(const T* __restrict__ xc, T* __restric
 // S <- (q - q_old) + S  (rmsbank.h:58-61; the "+ 0*0" of a real sample's |z|^2 is exact for q >= 0 and dropped).
 // CAP: S after tick `je` of the tile (0 <= je < TILE) is captured in s_at_je for the envelope row; without CAP
 // the caller takes S at the end of the tile (rows that fall on tile ends, e.g. hop = 64 on aligned blocks).
-template <typename T, bool FMA, int TAPS, bool CAP>
-__device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* __restrict__ xlc, T* __restrict__ yrow,
+template <typename T, bool FMA, int TAPS, bool CAP, bool VF>
+__device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* __restrict__ xlc, T* __restrict__ yrow, T g,
                                             T b0, T b1, T b2, T a1, T a2, T p, T b0l, T b1l, T b2l, T a1l, T a2l, T pl,
                                             T& y1, T& y2, T& x1, T& x2, T& m1, T& m2, T& t2,
                                             T& y1l, T& y2l, T& x1l, T& x2l, T& m1l, T& m2l, T& t2l,
@@ -213,8 +213,9 @@ __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* _
             const T yl = ru_sample<T, FMA, TAPS>(xlq[q & 1][j], b0l, b1l, b2l, a1l, a2l, pl, y1l, y2l, x1l, x2l, m1l, m2l, t2l);
             rsum = A::add(A::sub(A::mul(yy[j], yy[j]), A::mul(yl, yl)), rsum);
             if (CAP && 4 * q + j == je) s_at_je = rsum;
+            if (VF) yrow[(4 * q + j) * RowStride<T>::RS] = A::mul(yy[j], g);          // sample-major mixdown term (yrow = tile + lane)
         }
-        st4<T>(yrow + 4 * q, yy);
+        if (!VF) st4<T>(yrow + 4 * q, yy);
     }
 }
 
@@ -247,7 +248,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
     constexpr int RS = RowStride<T>::RS;
-    constexpr bool VF = !FMA && !BANDS && ENV == 0;          // tiles hold the mixdown terms, sample-major
+    constexpr bool VF = !FMA && !BANDS && ENV != 1;          // tiles hold the mixdown terms, sample-major (the ring followers read y back)
     const FbK1Params<T>& P = Q.k;
     const int W = Q.W;
     const int NS = s_warps(W);
@@ -488,7 +489,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
                     mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
                     T unused = (T)0;                                                                            \
-                    ru_tile_env<T, FMA, TP, false>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, \
+                    ru_tile_env<T, FMA, TP, false, VF>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, \
                                                    y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, -1, unused); \
                     hop_left -= TILE;                                                                           \
                     if (hop_left == 0) {                                                                        \
@@ -509,6 +510,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 continue;
             }
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
+            T ykeep[(VF && ENV == 2) ? TILE : 1];      // slow path of the replica followers only (local memory)
             if (kc == 0) mbar_wait(&x_full[xb], xpar);
             mbar_wait(&ye[yb], ypar ^ 1u);
             const T* xc = xs + xb * XT + kc * TILE;
@@ -522,14 +524,14 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 T s_je = (T)0;
                 if (je < 0 || je == TILE - 1) {
                     // no row, or the row falls on the tile's last tick: S at the end of the tile is what is needed
-                    if (taps == 2) ru_tile_env<T, FMA, 2, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else if (taps == 1) ru_tile_env<T, FMA, 1, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else ru_tile_env<T, FMA, 0, false>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    if (taps == 2) ru_tile_env<T, FMA, 2, false, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, false, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, false, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
                     s_je = rsum;
                 } else {
-                    if (taps == 2) ru_tile_env<T, FMA, 2, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else if (taps == 1) ru_tile_env<T, FMA, 1, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
-                    else ru_tile_env<T, FMA, 0, true>(xc, xlc, yrow, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    if (taps == 2) ru_tile_env<T, FMA, 2, true, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else if (taps == 1) ru_tile_env<T, FMA, 1, true, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
+                    else ru_tile_env<T, FMA, 0, true, VF>(xc, xlc, yrow, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, je, s_je);
                 }
                 if (je >= 0) {
                     if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(s_je, wT));   // rmsbank.h:64
@@ -539,7 +541,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 hop_left -= TILE;
                 tt = TILE;
                 fused = true;
-            } else if (conv && tn == TILE) {
+            } else if (conv && tn == TILE && !(VF && ENV == 2)) {
                 // whole tile unrolled; `taps` is uniform, so pick the specialised body once per tile
                 if (VF) {
                     if (taps == 2) ru_tile_v<T, FMA, 2>(xc, yrow, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2);
@@ -573,8 +575,9 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 x2 = x1; x1 = x0;
                 if (VF) yrow[tt * RS] = A::mul(y, g);                              // filterbank.h:130  y_n * g_n
                 else yrow[tt] = y;
+                if (VF && ENV == 2) ykeep[tt] = y;                                 // the follower below needs y itself
             }
-            if (!conv || tn != TILE) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }
+            if (!conv || tn != TILE || (VF && ENV == 2 && !fused)) { m1 = A::mul(b0, x1); m2 = A::mul(b0, x2); t2 = A::mul(a2, y2); }   // the per-sample loop ran
             if (!conv) conv = __all_sync(0xffffffffu, A::muladd(s_p, p, cp) == p && (!VF || A::muladd(s_g, g, cg) == g));
             if (ENV == 2 && !fused) {
                 // replica + follower, sample by sample (stream start, smoothers still moving, ragged tile, hop < TILE)
@@ -602,7 +605,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                         y2l = y1l; y1l = yl;
                         x2l = x1l; x1l = x0;
                     }
-                    const T y = yrow[j];
+                    const T y = VF ? ykeep[j] : yrow[j];
                     rsum = A::add(A::sub(A::mul(y, y), A::mul(yl, yl)), rsum);     // rmsbank.h:58-61
                     if (--hop_left == 0) {
                         if (ok && Q.env) Q.env[((size_t)s * Q.env_rows + env_row) * N + n] = A::sqrt(A::div(rsum, wT));   // :64
