@@ -25,6 +25,7 @@ namespace chain {
 struct Params {
     unsigned long long* ring;           // local links: link (s, c), c = 1..G-1, at ring + ((s*G + c) << ring_log2) * WPS
     unsigned long long* credit;         // [S*G] consumed virtual position of link (s, c), written by its reader
+    unsigned long long* credit_w;       // [S*G][CW] the same per reading warp, for links read by several warps (tile k by warp k mod n)
     unsigned long long* inbox;          // [S] rings the previous device writes (this device's memory); null: chain starts here
     unsigned long long* inbox_credit;   // [S] words in the previous device's memory where the head publishes its position
     unsigned long long* outbox;         // [S] rings in the next device's memory; null: the tail writes `out`
@@ -37,6 +38,7 @@ struct Params {
     int ordered;                        // 1: chained, index-order sum; 0: every CTA writes its own partial row (tree mode)
 };
 
+constexpr int CW = 16;                          // credit words per link in credit_w
 constexpr unsigned SPIN_LIMIT = 1u << 27;      // polls before the watchdog gives up (tens of seconds)
 
 // CTA's linear chain ticket (call from every thread; one atomic per CTA)

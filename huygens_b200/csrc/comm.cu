@@ -269,7 +269,7 @@ hg_status hg_fb_process_sharded(hg_fb* fb, hg_comm* c, const void* in, void* out
         // this handle's private rings may hold tags of another position sequence: start them clean
         HG_CUDA(cudaStreamSynchronize(st));
         if (fb->d_chain_ring) HG_CUDA(cudaMemsetAsync(fb->d_chain_ring, 0, fb->chain_ring_words * 8, st));
-        if (fb->d_chain_credit) HG_CUDA(cudaMemsetAsync(fb->d_chain_credit, 0, fb->chain_links * 8, st));
+        if (fb->d_chain_credit) HG_CUDA(cudaMemsetAsync(fb->d_chain_credit, 0, fb->chain_links * (1 + hg::chain::CW) * 8, st));
         fb->chain_owner = c;
     }
     fb->chain_vbase = c->vbase;

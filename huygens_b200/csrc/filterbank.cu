@@ -463,10 +463,10 @@ static hg_status chain_reserve(hg_fb* fb, size_t links, cudaStream_t st) {
         fb->d_chain_ring = nullptr; fb->d_chain_credit = nullptr; fb->chain_links = 0;
         const size_t words = (links << lg) * wps;
         cudaError_t ce;
-        if ((ce = cudaMalloc(&fb->d_chain_ring, words * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&fb->d_chain_credit, links * 8)) != cudaSuccess)
+        if ((ce = cudaMalloc(&fb->d_chain_ring, words * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&fb->d_chain_credit, links * (1 + chain::CW) * 8)) != cudaSuccess)
             return fail(HG_ERR_NOMEM, "ordered mixdown: %zu links of %d samples: %s", links, 1 << lg, cudaGetErrorString(ce));
         HG_CUDA(cudaMemsetAsync(fb->d_chain_ring, 0, words * 8, st));
-        HG_CUDA(cudaMemsetAsync(fb->d_chain_credit, 0, links * 8, st));
+        HG_CUDA(cudaMemsetAsync(fb->d_chain_credit, 0, links * (1 + chain::CW) * 8, st));
         fb->chain_links = links; fb->chain_ring_log2 = lg; fb->chain_ring_words = words;
     }
     return HG_OK;
@@ -476,9 +476,9 @@ template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st) {
     int F, groups;
     k1_config(fb, &F, &groups);
-    int ru_W = 0, ru_cps = 0;
+    int ru_W = 0, ru_NS = 0, ru_cps = 0;
     if (F == -2) {
-        fb_ru_config<T>(fb, &ru_W, &ru_cps);
+        fb_ru_config<T>(fb, d_bands != nullptr, &ru_W, &ru_NS, &ru_cps);
         groups = ru_cps;                     // partial-sum rows per stream: one per CTA
     }
     fb->last_F = F;
@@ -551,6 +551,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.chain = fb->cur_peer;
         P.chain.ring = (unsigned long long*)fb->d_chain_ring;
         P.chain.credit = fb->d_chain_credit;
+        P.chain.credit_w = fb->d_chain_credit + fb->chain_links;      // per-warp credit words behind the per-link ones
         P.chain.vbase = fb->chain_vbase;
         P.chain.ticket = fb->d_ticket;
         P.chain.ticket_base = fb->ticket_base;
@@ -584,7 +585,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
                     E.lag_par = (const T*)fb->d_lag_par; E.lag_taps = fb->lag_taps;
                 }
             }
-            rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_cps, st, fb->cur_env ? &E : nullptr);
+            rc = fb_launch_exact_ru<T>(fma, d_bands != nullptr, P, ru_W, ru_NS, ru_cps, st, fb->cur_env ? &E : nullptr);
         }
         else if (d_bands) rc = fma ? launch_k1_F<T, true, K1_NT, true>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, true>(F, P, groups, st);
         else rc = fma ? launch_k1_F<T, true, K1_NT, false>(F, P, groups, st) : launch_k1_F<T, false, K1_NT, false>(F, P, groups, st);

@@ -131,10 +131,10 @@ template <typename T> struct FbEnvArgs {
     int lag_taps = 0;
 };
 template <typename T>
-hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int ctas_per_stream, cudaStream_t st,
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int NS, int ctas_per_stream, cudaStream_t st,
                              const FbEnvArgs<T>* env = nullptr);
 template <typename T>
-void fb_ru_config(const hg_fb* fb, int* W_out, int* ctas_per_stream_out);
+void fb_ru_config(const hg_fb* fb, bool bands, int* W_out, int* NS_out, int* ctas_per_stream_out);
 template <typename T>
 hg_status fb_process_scan(hg_fb* fb, const T* d_in, T* d_out, size_t L, cudaStream_t st);
 

@@ -34,7 +34,11 @@ namespace hg {
 namespace ru {
 
 constexpr int TILE = 32;      // samples per hand-over tile (S lane = sample)
-constexpr int NB = 2;         // tile ring depth per RU warp
+constexpr int NB = 2;         // tile ring depth per RU warp (y tiles)
+#ifndef HG_RU_NB_VF
+#define HG_RU_NB_VF 2
+#endif
+constexpr int NB_VF = HG_RU_NB_VF;   // ... of a term-tile kernel (no gain tiles: the shared memory goes to a deeper ring)
 constexpr int XT = 1024;      // input chunk
 constexpr int XB = 2;         // input ring depth
 constexpr int W_MAX = 14;     // RU warps per CTA
@@ -42,8 +46,31 @@ constexpr int W_MAX_ENV = 8;  // ... with fused envelope followers: fewer warps,
 constexpr int GPS = 2;        // RU warps served by one S warp: an S warp must not need more than its fair share
                               // of its scheduler's issue slots, or the RU warps starve behind it
 constexpr int NS_MAX = (W_MAX + GPS - 1) / GPS;
-constexpr int PD = 4;         // depth of the running-row hand-over between consecutive S warps
+constexpr int YB_MAX = 14;    // hand-over barrier pairs per RU warp (>= NB and >= the S warps of a term-tile kernel)
+#ifndef HG_RU_PD
+#define HG_RU_PD 4
+#endif
+#ifndef HG_RU_GD
+#define HG_RU_GD 2
+#endif
+constexpr int GD = HG_RU_GD;  // inbound packets (tiles) the gateway keeps in flight
+constexpr int PD = HG_RU_PD;         // depth of the running-row hand-over between consecutive S warps
+// S warps of a CTA.  y tiles: an S warp serves GPS RU warps and hands the running row to the next S warp.  Term tiles
+// (VF): S warp j adds ALL the CTA's filters for the tiles k = j (mod NS); its additions are one dependent chain whose
+// every link waits ~10-20 cycles for an issue slot among the RU warps, so the S warps' number is what bounds the
+// mixdown's throughput: as many as the register file allows (fb_ru_config), at most one per RU warp.
 __host__ __device__ constexpr int s_warps(int W) { return (W + GPS - 1) / GPS; }
+#ifndef HG_RU_NS_CAP
+#define HG_RU_NS_CAP 8
+#endif
+constexpr int CTA_WARPS_MAX = 24;   // 24 warps x 32 lanes x 80 registers fit the 65 536 of an SM (ptxas grants 25 warps only 72)
+__host__ __device__ constexpr int s_warps_vf(int W, int per_sm) {
+    const int room = CTA_WARPS_MAX / per_sm - W - 1;
+    const int cap = W < HG_RU_NS_CAP ? W : HG_RU_NS_CAP;
+    return room < cap ? room : cap;
+}
+// which kernels keep the mixdown TERMS fl(y*g) in their tiles (the ring followers read y back; fma needs y and g)
+template <bool FMA, bool BANDS, int ENV> struct TermTiles { static constexpr bool value = !FMA && !BANDS && ENV != 1; };
 
 template <typename T> struct RowStride;      // RS*sizeof(T)/16 odd: conflict-free 128-bit rows
 template <> struct RowStride<float> { static constexpr int RS = TILE + 4; };
@@ -83,6 +110,9 @@ __device__ __forceinline__ bool mbar_poll(unsigned long long* b, unsigned parity
         : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     return ok != 0;
 }
+// makes the instruction stream wait, at this point, until the load that produces x has returned
+__device__ __forceinline__ void reg_fence(float x) { asm volatile("" ::"f"(x) : "memory"); }
+__device__ __forceinline__ void reg_fence(double x) { asm volatile("" ::"d"(x) : "memory"); }
 template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&x)[4]);
 template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&x)[4]) {
     float4 v = *reinterpret_cast<const float4*>(p);
@@ -105,17 +135,17 @@ template <> __device__ __forceinline__ void st4<double>(double* p, const double 
 //   xs[XB][XT] | y[W][NB][32*RS] | gt[NS][32*RS] | gs[NS][GPS][32] | psum[NS][PD][32] | barriers
 template <typename T> struct Layout {
     static constexpr int RS = RowStride<T>::RS;
-    int W, NS, LAG;       // LAG: the replica followers add a second input ring
-    __host__ __device__ explicit Layout(int w, bool lag = false) : W(w), NS(s_warps(w)), LAG(lag ? 1 : 0) {}
+    int W, NS, LAG, NBk, GT;       // LAG: the replica followers add a second input ring; NBk: tile slots per RU warp; GT: gain tiles
+    __host__ __device__ Layout(int w, int ns, bool lag, bool vf) : W(w), NS(ns), LAG(lag ? 1 : 0), NBk(vf ? NB_VF : NB), GT(vf ? 0 : 1) {}
     __host__ __device__ size_t xs_off() const { return 0; }
     __host__ __device__ size_t y_off() const { return sizeof(T) * XB * XT; }
-    __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NB * 32 * RS; }
-    __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * NS * 32 * RS; }
+    __host__ __device__ size_t gt_off() const { return y_off() + sizeof(T) * (size_t)W * NBk * 32 * RS; }
+    __host__ __device__ size_t gs_off() const { return gt_off() + sizeof(T) * GT * NS * 32 * RS; }
     __host__ __device__ size_t ps_off() const { return gs_off() + sizeof(T) * NS * GPS * 32; }
     __host__ __device__ size_t xl_off() const { return (ps_off() + sizeof(T) * PD * NS * 32 + 15) & ~(size_t)15; }
     __host__ __device__ size_t yl_off() const { return xl_off() + sizeof(T) * (size_t)LAG * XB * XT; }
     __host__ __device__ size_t bar_off() const { return (yl_off() + 15) & ~(size_t)15; }
-    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * NB + 2 * PD * NS); }
+    __host__ __device__ size_t bytes() const { return bar_off() + 8 * (size_t)(2 * XB + 2 * W * YB_MAX + 2 * PD * NS); }
 };
 
 }  // namespace ru
@@ -222,6 +252,7 @@ __device__ __forceinline__ void ru_tile_env(const T* __restrict__ xc, const T* _
 template <typename T> struct FbRuParams {
     FbK1Params<T> k;
     int W;            // RU warps per CTA
+    int NS;           // S warps per CTA
     int cps;          // CTAs per stream = ceil(ceil(N/32) / W)
     // ENV variant: per-band RMSbank envelope followers fused behind the filters (src/rmsbank.h:54-74 on
     // the real band outputs: q = y^2, S <- (q - q[t-width]) + S, env = sqrt(S / width))
@@ -243,17 +274,18 @@ template <typename T> struct FbRuParams {
 
 // ENV: 0 no followers; 1 followers with the ring of y^2 in HBM; 2 followers with lagged replicas
 template <typename T, bool FMA, bool BANDS, int ENV>
-__global__ void __launch_bounds__(ENV == 1 ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV) + 1) * 32 : (ru::W_MAX + ru::NS_MAX + 1) * 32, 1)
+__global__ void __launch_bounds__(ENV == 1 ? (ru::W_MAX_ENV + ru::s_warps(ru::W_MAX_ENV) + 1) * 32 : (ru::TermTiles<FMA, BANDS, ENV>::value ? ru::CTA_WARPS_MAX : ru::W_MAX + ru::NS_MAX + 1) * 32, 1)
 fb_exact_ru_kernel(FbRuParams<T> Q) {
     using namespace ru;
     typedef Ar<T, FMA> A;
     constexpr int RS = RowStride<T>::RS;
-    constexpr bool VF = !FMA && !BANDS && ENV != 1;          // tiles hold the mixdown terms, sample-major (the ring followers read y back)
+    constexpr bool VF = TermTiles<FMA, BANDS, ENV>::value;   // tiles hold the mixdown terms, sample-major
+    constexpr int NB = VF ? ru::NB_VF : ru::NB;              // tile slots per RU warp
     const FbK1Params<T>& P = Q.k;
     const int W = Q.W;
-    const int NS = s_warps(W);
+    const int NS = Q.NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Layout<T> lay(W, ENV == 2);
+    const Layout<T> lay(W, NS, ENV == 2, VF);
     T* xs = reinterpret_cast<T*>(smem_raw + lay.xs_off());
     T* xls = reinterpret_cast<T*>(smem_raw + lay.xl_off());          // ENV == 2: lagged input ring
     T* ytiles = reinterpret_cast<T*>(smem_raw + lay.y_off());
@@ -263,12 +295,21 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + lay.bar_off());
     unsigned long long* x_full = bars;                      // [XB]
     unsigned long long* x_empty = bars + XB;                // [XB]
-    unsigned long long* y_full = bars + 2 * XB;             // [W][NB]
-    unsigned long long* y_empty = bars + 2 * XB + W * NB;   // [W][NB]
-    unsigned long long* ps_full = bars + 2 * XB + 2 * W * NB;       // [NS][PD] running row of S warp i ready for S warp i+1
+    // Tile hand-over barriers of RU warp w: tile k uses pair k % YB.  y tiles: YB = NB, one pair per tile slot.  Term
+    // tiles: YB = NS, one pair per S warp (S warp j takes the tiles k = j mod NS, so every barrier is waited on by one
+    // warp, phase after phase — a waiter that skipped a phase would misread the parity); the slot is still k % NB.
+    const int YB = VF ? NS : NB;
+    unsigned long long* y_full = bars + 2 * XB;                  // [W][YB]
+    unsigned long long* y_empty = bars + 2 * XB + W * YB_MAX;    // [W][YB]
+    unsigned long long* ps_full = bars + 2 * XB + 2 * W * YB_MAX;    // [NS][PD] running row of S warp i ready for S warp i+1
     unsigned long long* ps_empty = ps_full + PD * NS;                // [NS][PD] ... consumed
 
+#ifdef HG_EXP_S_FIRST
+    const int lane = threadIdx.x & 31, hw_warp = threadIdx.x >> 5;
+    const int warp = hw_warp <= NS ? W + hw_warp : hw_warp - (NS + 1);       // experiment: S and G warps get the lowest warp ids
+#else
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#endif
     // chain position = arrival order (chain.cuh): CTA (s, cta) owns the filter groups [cta W, cta W + W) of stream s
     const unsigned ticket = chain::take_ticket(P.chain);
     const int cta = (int)(ticket % gridDim.x), s = (int)(ticket / gridDim.x);
@@ -285,7 +326,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < XB; i++) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], w_here); }
-        for (int i = 0; i < W * NB; i++) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < W * YB; i++) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
         for (int i = 0; i < PD * NS; i++) { mbar_init(&ps_full[i], 1); mbar_init(&ps_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -299,6 +340,10 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
     const bool head = !ordered || cta == 0, tail = !ordered || cta == G - 1;
     const bool has_in = ordered && summing && (!head || C.inbox != nullptr);
     constexpr int WPS = chain::Words<T>::WPS;
+    // Term tiles, long chains: the links between the CTAs of this launch are polled by the S warps themselves (see the S
+    // role); short chains of many streams (BASELINE configs[3]: 4 CTAs per stream) keep the gateway warp, whose
+    // prefetch costs the few S warps of those CTAs nothing.
+    const bool dlinks = VF && G > 8;
 
     if (warp == W + NS) {
         // ------------------------------ G: input loader + chain gateway ------------------------------
@@ -313,17 +358,27 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             if (!head) pin.open(C.ring + (((size_t)s * G + cta) << C.ring_log2) * WPS, C.credit + (size_t)s * G + cta, C);
             else pin.open(C.inbox + ((size_t)s << C.ring_log2) * WPS, C.inbox_credit + s, C);
         }
-        typename chain::Port<T, 1>::Raw r0, r1;
-        const int gtiles = has_in ? ntiles : 0;
-        if (gtiles > 0 && lane < L) pin.issue(C, lane, r0);
-        if (gtiles > 1 && TILE + lane < L) pin.issue(C, TILE + lane, r1);
+        typename chain::Port<T, 1>::Raw rq[GD];            // polls in flight: tiles gk .. gk + GD - 1
+        // term tiles: the S warps poll the links between CTAs themselves (below); the gateway only serves a device's inbox
+        const int gtiles = (has_in && (!dlinks || head)) ? ntiles : 0;
+#pragma unroll
+        for (int i = 0; i < GD; i++)
+            if (i < gtiles && (long)i * TILE + lane < L) pin.issue(C, (long)i * TILE + lane, rq[i]);
         unsigned long long* gfull = ps_full + (NS - 1) * PD;        // the hand-over slots of the (unused) link after the last S warp
         unsigned long long* gempty = ps_empty + (NS - 1) * PD;
         T* gslot = psum + (size_t)(NS - 1) * PD * 32;
         int c = 0, gk = 0;
         unsigned spins = 0;
+#ifdef HG_PROF_G
+        long long g_slot = 0, g_data = 0, g_t = clock64();
+#endif
         while (c < nchunks || gk < gtiles) {
             bool progress = false;
+#ifdef HG_PROF_G
+            { const long long now = clock64();
+              if (gk < gtiles) { if (!mbar_poll(&gempty[gk % PD], (unsigned)(((gk / PD) & 1) ^ 1))) g_slot += now - g_t; else g_data += now - g_t; }
+              g_t = now; }
+#endif
             const int b = c % XB;
             if (c < nchunks && mbar_poll(&x_empty[b], (unsigned)(((c / XB) & 1) ^ 1))) {
                 const long base = (long)c * XT;
@@ -348,33 +403,47 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 c++;
                 progress = true;
             }
-            const int pb = gk % PD;
-            if (gk < gtiles && mbar_poll(&gempty[pb], (unsigned)(((gk / PD) & 1) ^ 1))) {
+            // Gateway: up to GD tiles are accepted per pass, and every packet of the window that has not arrived is
+            // polled again in the same pass — a poll is an L2 round trip (1-2 k cycles under load), so a gateway that
+            // asked for one tile per round trip would cap the whole chain at a tile per round trip.
+#pragma unroll
+            for (int rep = 0; rep < GD; rep++) {
+                const int pb = gk % PD;
+                if (!(gk < gtiles && mbar_poll(&gempty[pb], (unsigned)(((gk / PD) & 1) ^ 1)))) break;
                 const long t = (long)gk * TILE + lane;
-                const bool got = !(t < L) || pin.ready(C, t, r0);
-                if (__all_sync(0xffffffffu, got)) {
-                    T v[1];
-                    memcpy(v, r0.w, sizeof(v));
-                    gslot[pb * 32 + lane] = v[0];
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&gfull[pb]);
-                        pin.release(C, (long)(gk + 1) * TILE);       // the packet is in shared memory: its ring slot is free
-                    }
-                    gk++;
-                    r0 = r1;
-                    if (gk + 1 < gtiles && (long)(gk + 1) * TILE + lane < L) pin.issue(C, (long)(gk + 1) * TILE + lane, r1);
-                    progress = true;
-                } else if (!got) {
-                    pin.issue(C, t, r0);                             // poll again (this lane's packet only)
+                const bool got = !(t < L) || pin.ready(C, t, rq[0]);
+                if (!__all_sync(0xffffffffu, got)) break;
+                T v[1];
+                memcpy(v, rq[0].w, sizeof(v));
+                gslot[pb * 32 + lane] = v[0];
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&gfull[pb]);
+                    pin.release(C, (long)(gk + 1) * TILE);       // the packet is in shared memory: its ring slot is free
                 }
+                gk++;
+#pragma unroll
+                for (int i = 0; i + 1 < GD; i++) rq[i] = rq[i + 1];
+                if (gk + GD - 1 < gtiles && (long)(gk + GD - 1) * TILE + lane < L) pin.issue(C, (long)(gk + GD - 1) * TILE + lane, rq[GD - 1]);
+                progress = true;
+            }
+#pragma unroll
+            for (int i = 0; i < GD; i++) {                       // poll again what is still missing (this lane's packets only)
+                const long t = (long)(gk + i) * TILE + lane;
+                if (gk + i < gtiles && t < L && !(progress && i == GD - 1) && !pin.ready(C, t, rq[i])) pin.issue(C, t, rq[i]);
             }
             if (progress) spins = 0;
             else {
-                __nanosleep(32);          // nothing to do right now: leave the issue and shared-memory pipes to the other roles
+#ifndef HG_RU_GSLEEP
+#define HG_RU_GSLEEP 32
+#endif
+                __nanosleep(HG_RU_GSLEEP);          // nothing to do right now: leave the issue and shared-memory pipes to the other roles
                 if (++spins > chain::SPIN_LIMIT / 8) { *C.error = 1; break; }
             }
         }
+#ifdef HG_PROF_G
+        if (HG_PROF_ON(P) && lane == 0) { long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8; q[6] = g_slot; q[7] = g_data; }
+#endif
         return;
     }
     if (warp < W) {
@@ -399,10 +468,14 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         const T cg = VF ? A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0) : (T)0, s_g = P.s_g;
         if (VF) conv = conv && __all_sync(0xffffffffu, A::muladd(s_g, g, cg) == g);     // `conv`: both smoothers at their fixed point
         T* ybase = ytiles + (size_t)warp * NB * 32 * RS + (VF ? lane : lane * RS);
-        unsigned long long* yf = y_full + warp * NB;
-        unsigned long long* ye = y_empty + warp * NB;
+        unsigned long long* yf = y_full + warp * YB;
+        unsigned long long* ye = y_empty + warp * YB;
         int xb = 0, yb = 0, kc = 0;
-        unsigned xpar = 0, ypar = 0;
+        unsigned xpar = 0;
+        // tile k: slot yb = k % NB; filled -> yf[fi], fi = k % YB; before writing, the slot's previous tile k - NB must have
+        // been taken: ye[ei], ei = (k - NB) % YB, phase (k - NB) / YB (a fresh barrier passes the wait for "phase -1")
+        int fi = 0, ei = (YB - NB % YB) % YB;
+        unsigned epar = 1;
         T t2 = A::mul(a2, y2);
         // ENV: envelope follower state of this lane
         T rsum = (ENV && ok) ? Q.rms_sum[si] : (T)0;
@@ -449,9 +522,14 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 qo[j] = (j < cnt0) ? ring[(size_t)pj * 32] : (T)0;
             }
         }
-        static_assert(NB == 2, "the steady-state loop toggles between two tile slots");
         long long pf_gate = 0, pf_x = 0;
         const long long pf_t0 = HG_PROF_ON(P) ? clock64() : 0;
+#ifdef HG_EXP_HEAD_NS
+        const bool throttle = ordered && summing && head && G > 1;
+#define HG_HEAD_THROTTLE if (throttle) __nanosleep(HG_EXP_HEAD_NS);
+#else
+#define HG_HEAD_THROTTLE
+#endif
         for (int k = 0; k < ntiles; k++) {
             if (ENV == 0 && conv && kc == 0 && (long)(k + TPC) * TILE <= L) {
                 // steady state: a whole input chunk of full tiles with converged smoothers.  Nothing but the two
@@ -462,14 +540,16 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
 #define HG_RU_CHUNK(TP)                                                                                          \
                 _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
                     const long long pc0 = HG_PROF_ON(P) ? clock64() : 0;                                               \
-                    mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
+                    mbar_wait(&ye[ei], epar);                                                                   \
                     if (HG_PROF_ON(P)) pf_gate += clock64() - pc0;                                                     \
+                    HG_HEAD_THROTTLE                                                                            \
                     if (VF) ru_tile_v<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, g, y1, y2, x1, x2, m1, m2, t2); \
                     else ru_tile<T, FMA, TP>(xcb + i * TILE, ybase + yb * 32 * RS, b0, b1, b2, a1, a2, p, y1, y2, x1, x2, m1, m2, t2); \
                     __syncwarp();                                                                               \
-                    if (lane == 0) mbar_arrive(&yf[yb]);                                                        \
-                    ypar ^= (unsigned)yb;                                                                       \
-                    yb ^= 1;                                                                                    \
+                    if (lane == 0) mbar_arrive(&yf[fi]);                                                        \
+                    if (++yb == NB) yb = 0;                                                                     \
+                    if (++fi == YB) fi = 0;                                                                     \
+                    if (++ei == YB) { ei = 0; epar ^= 1u; }                                                     \
                 }
                 if (taps == 2) { HG_RU_CHUNK(2) } else if (taps == 1) { HG_RU_CHUNK(1) } else { HG_RU_CHUNK(0) }
 #undef HG_RU_CHUNK
@@ -487,7 +567,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 const T* xlcb = xls + xb * XT;
 #define HG_RU_CHUNK_ENV(TP)                                                                                      \
                 _Pragma("unroll 1") for (int i = 0; i < TPC; i++) {                                             \
-                    mbar_wait(&ye[yb], ypar ^ 1u);                                                              \
+                    mbar_wait(&ye[ei], epar);                                                                   \
                     T unused = (T)0;                                                                            \
                     ru_tile_env<T, FMA, TP, false, VF>(xcb + i * TILE, xlcb + i * TILE, ybase + yb * 32 * RS, g, b0, b1, b2, a1, a2, p, b0l, b1l, b2l, a1l, a2l, pl, \
                                                    y1, y2, x1, x2, m1, m2, t2, y1l, y2l, x1l, x2l, m1l, m2l, t2l, rsum, -1, unused); \
@@ -498,9 +578,10 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                         hop_left = Q.hop;                                                                       \
                     }                                                                                           \
                     __syncwarp();                                                                               \
-                    if (lane == 0) mbar_arrive(&yf[yb]);                                                        \
-                    ypar ^= (unsigned)yb;                                                                       \
-                    yb ^= 1;                                                                                    \
+                    if (lane == 0) mbar_arrive(&yf[fi]);                                                        \
+                    if (++yb == NB) yb = 0;                                                                     \
+                    if (++fi == YB) fi = 0;                                                                     \
+                    if (++ei == YB) { ei = 0; epar ^= 1u; }                                                     \
                 }
                 if (taps == 2) { HG_RU_CHUNK_ENV(2) } else if (taps == 1) { HG_RU_CHUNK_ENV(1) } else { HG_RU_CHUNK_ENV(0) }
 #undef HG_RU_CHUNK_ENV
@@ -512,7 +593,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             const int tn = (k == ntiles - 1) ? last_tn : TILE;
             T ykeep[(VF && ENV == 2) ? TILE : 1];      // slow path of the replica followers only (local memory)
             if (kc == 0) mbar_wait(&x_full[xb], xpar);
-            mbar_wait(&ye[yb], ypar ^ 1u);
+            mbar_wait(&ye[ei], epar);
             const T* xc = xs + xb * XT + kc * TILE;
             T* yrow = ybase + yb * 32 * RS;
             int tt = 0;
@@ -669,10 +750,12 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             __syncwarp();
             const bool chunk_done = (kc == TPC - 1) || (k == ntiles - 1);
             if (lane == 0) {
-                mbar_arrive(&yf[yb]);
+                mbar_arrive(&yf[fi]);
                 if (chunk_done) mbar_arrive(&x_empty[xb]);
             }
-            if (++yb == NB) { yb = 0; ypar ^= 1u; }
+            if (++yb == NB) yb = 0;
+            if (++fi == YB) fi = 0;
+            if (++ei == YB) { ei = 0; epar ^= 1u; }
             if (++kc == TPC) { kc = 0; if (++xb == XB) { xb = 0; xpar ^= 1u; } }
         }
         if (ok) {
@@ -682,14 +765,165 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             if (ENV == 2) { Q.lag_state[0 * SN + si] = y1l; Q.lag_state[1 * SN + si] = y2l; Q.lag_state[2 * SN + si] = pl; }
         }
         if (cta == 0 && warp == 0 && lane == 0 && L > 0) { P.xh_out[2 * s] = x1; P.xh_out[2 * s + 1] = x2; }
+#ifdef HG_PROF_G
+        if (HG_PROF_ON(P) && lane == 0 && warp == 0) {
+#else
         if (HG_PROF_ON(P) && lane == 0 && (warp == 0 || warp == w_here - 1)) {
+#endif
             long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8 + (warp == 0 ? 4 : 6);
             q[0] = pf_gate; q[1] = warp == 0 ? pf_x : clock64() - pf_t0;
+#ifdef HG_PROF_G
+            { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); q[1] = (long long)smid * L; }
+#endif
         }
     } else {
-        // ------------------------------ S: mixdown, gains, input ring ------------------------------
+        // ------------------------------ S: mixdown ------------------------------
         const int sidx = warp - W;                          // 0 .. NS-1
         if (sidx >= NS) return;
+        if constexpr (VF) {
+            // Term tiles.  S warp j adds ALL the CTA's filters, in index order, onto the running row of the tiles
+            // k = j (mod NS): it walks the RU warps' tiles of that tile index (lane = sample, this lane's 32 terms of an
+            // RU warp are one row), the terms fetched one batch ahead of the additions and every tile slot given back
+            // as soon as its terms are in registers.  The CTA is ONE stage of the chain — no hand-over between S
+            // warps; the row comes from the gateway's slot k % PD and leaves for the next CTA / device / `out`.
+            constexpr int CH = 64 / (int)sizeof(T), NBAT = 32 / CH;     // terms per batch, batches per RU warp
+            // Links between CTAs of this launch are read by the S warp that needs the tile (NS polls in flight per link: a
+            // poll is an L2 round trip of 1-2 k cycles and strong loads of one warp do not overlap, so a single polling
+            // warp would cap the chain at a tile per round trip) — each reading warp publishes its own credit word, and
+            // the warp that writes tile k checks the word of the warp that read tile k - ring.  A device's inbox is
+            // still served by the gateway warp (one credit word: the writer may be another kernel).
+            const bool direct = dlinks && ordered && summing && !head;
+            const bool via_g = has_in && !direct;
+            chain::Port<T, 1> pin, pout;
+            typename chain::Port<T, 1>::Raw raw;
+            if (direct) pin.open(C.ring + (((size_t)s * G + cta) << C.ring_log2) * WPS, C.credit_w + ((size_t)s * G + cta) * chain::CW + sidx, C);
+            if (ordered && summing) {
+                if (!tail) {
+                    const int ring_tiles = (1 << C.ring_log2) / TILE;
+                    const int reader = ((sidx - ring_tiles % NS) % NS + NS) % NS;       // the next CTA's warp that read tile k - ring_tiles
+                    pout.open(C.ring + (((size_t)s * G + cta + 1) << C.ring_log2) * WPS,
+                              dlinks ? C.credit_w + ((size_t)s * G + cta + 1) * chain::CW + reader : C.credit + (size_t)s * G + cta + 1, C);
+                } else if (C.outbox) pout.open(C.outbox + ((size_t)s << C.ring_log2) * WPS, C.outbox_credit + s, C);
+            }
+            T* out_row = nullptr;
+            if (P.out && tail && !pout.on())
+                out_row = ordered ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)cta * P.S + s) * (size_t)L);   // tree mode: one partial row per CTA
+            const T* carry = (ordered && head && !has_in && P.carry_in) ? P.carry_in + (size_t)s * P.carry_stride : nullptr;
+            const bool dist = P.dist != 0;
+            const int gl = NS - 1;                          // the gateway's hand-over slots
+            const int nb = w_here * NBAT;                   // batches per tile (even)
+            long long pf_in = 0, pf_y = 0, pf_mix = 0, pf_out = 0;
+            if (direct && sidx < ntiles && (long)sidx * TILE + lane < L) pin.issue(C, (long)sidx * TILE + lane, raw);
+#pragma unroll 1
+            for (int k = sidx; k < ntiles; k += NS) {
+                const int tn = (k == ntiles - 1) ? last_tn : TILE;
+                const long tg = (long)k * TILE;
+                const int yb = k % NB;                          // tile slot; barrier pair of this S warp: sidx = k % NS
+                const unsigned ypar = (unsigned)((k / NS) & 1);
+                const int pb = k % PD;
+                const unsigned ppar = (unsigned)((k / PD) & 1);
+                const T* row0 = ytiles + (size_t)yb * 32 * RS + lane * RS;      // this lane's row in RU warp 0's slot
+                long long pc0 = HG_PROF_ON(P) ? clock64() : 0, pc1;
+                auto fetch = [&](int b, T(&v)[CH]) {
+                    const int w = b / NBAT, part = b % NBAT;
+                    if (part == 0) {
+                        if (HG_PROF_ON(P)) { const long long q0 = clock64(); mbar_wait(&y_full[w * YB + sidx], ypar); pf_y += clock64() - q0; }
+                        else mbar_wait(&y_full[w * YB + sidx], ypar);
+                    }
+                    const T* src = row0 + (size_t)w * NB * 32 * RS + part * CH;
+#pragma unroll
+                    for (int q = 0; q < CH / 4; q++) ld4<T>(src + 4 * q, *reinterpret_cast<T(*)[4]>(&v[4 * q]));
+                };
+                auto landed = [&](int b, const T(&v)[CH]) {       // batch b is in registers: its tile slot is free after the last part
+                    if (b % NBAT == NBAT - 1) {
+                        reg_fence(v[CH - 1]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&y_empty[(b / NBAT) * YB + sidx]);
+                    }
+                };
+                T va[CH], vb[CH];
+                if (!summing) {                                   // nothing to add: just recycle the slots
+                    for (int w = 0; w < w_here; w++) {
+                        mbar_wait(&y_full[w * YB + sidx], ypar);
+                        if (lane == 0) mbar_arrive(&y_empty[w * YB + sidx]);
+                    }
+                    continue;
+                }
+                fetch(0, va);
+                T acc = (T)0;
+                if (HG_PROF_ON(P)) pc0 = clock64();
+                if (direct) {
+                    const long t = tg + lane;
+                    bool got = !(t < L) || chain::Port<T, 1>::ready(C, t, raw);
+                    unsigned spins = 0;
+                    while (!__all_sync(0xffffffffu, got)) {
+                        if (!got) { pin.issue(C, t, raw); got = chain::Port<T, 1>::ready(C, t, raw); }
+                        if (++spins > chain::SPIN_LIMIT) { *C.error = 1; break; }
+                    }
+                    if (t < L) { T v[1]; memcpy(v, raw.w, sizeof(v)); acc = v[0]; }
+                    __syncwarp();
+                    if (lane == 0) pin.release(C, tg + TILE);
+                    // ask for this warp's next row now: the poll is in flight during the whole walk (stale if the CTA before
+                    // is not that far ahead; it is repeated above when the row is needed)
+                    if (k + NS < ntiles && t + (long)NS * TILE < L) pin.issue(C, t + (long)NS * TILE, raw);
+                } else if (via_g) {
+                    mbar_wait(&ps_full[gl * PD + pb], ppar);
+                    acc = psum[((size_t)gl * PD + pb) * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ps_empty[gl * PD + pb]);
+                } else if (carry) {
+                    if (lane < tn) acc = carry[tg + lane];
+                }
+                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_in += pc1 - pc0; pc0 = pc1; }
+                // acc = fl(v_l[t] + acc), l ascending over the CTA's filters: src/filterbank.h:130 (:137 with the per-band
+                // distortion).  Lanes past the bank's last filter wrote +-0 terms, which leave any sum unchanged.
+#pragma unroll 1
+                for (int b = 0; b < nb; b += 2) {
+                    fetch(b + 1, vb);
+                    if (dist) {
+#pragma unroll
+                        for (int l = 0; l < CH; l++) acc = A::add(acc, softclip_dev<T>(va[l]));
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < CH; l++) acc = A::add(va[l], acc);
+                    }
+                    landed(b + 1, vb);
+                    if (b + 2 < nb) fetch(b + 2, va);
+                    if (dist) {
+#pragma unroll
+                        for (int l = 0; l < CH; l++) acc = A::add(acc, softclip_dev<T>(vb[l]));
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < CH; l++) acc = A::add(vb[l], acc);
+                    }
+                }
+                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_mix += pc1 - pc0; pc0 = pc1; }
+                if (pout.on()) {
+                    pout.reserve(C, tg + TILE);
+                    T a1v[1] = {acc};
+                    pout.send(C, tg + lane, a1v);
+                } else if (out_row) {
+                    if (lane < tn) {
+                        if (P.epi.kind && ordered) acc = epilogue_dev<T>(P.epi, acc, P.dry_in[(size_t)s * P.in_stride + tg + lane]);
+                        out_row[tg + lane] = acc;
+                    }
+                }
+                if (HG_PROF_ON(P)) pf_out += clock64() - pc0;
+#ifdef HG_PROF_G
+                if (HG_PROF_ON(P) && lane == 0 && sidx == 1 && ((k / NS) & 31) == 0 && (k / NS) / 32 < 128) {     // progress stamps: tile k done at time t
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    P.prof[(size_t)(1024 + cta * 16) * 8 + (k / NS) / 32] = (long long)now;
+                }
+#endif
+            }
+            if (HG_PROF_ON(P) && lane == 0 && sidx == (NS > 1 ? 1 : 0)) {
+                long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8;
+                q[0] = pf_in; q[1] = pf_y; q[2] = pf_mix; q[3] = pf_out;
+            }
+            return;
+        }
+        // ---- y tiles (fused arithmetic, per-band rows, ring followers): the S warps own the mix gains and form a chain ----
         // RU warps served by this S warp: an even split of the CTA's active RU warps
         const int per = (w_here + NS - 1) / NS;
         const int wa = min(w_here, sidx * per), wb = min(w_here, wa + per);
@@ -702,7 +936,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         for (int i = 0; i < GPS; i++) {
             const int w = wa + i;
             const int n = (w_first + w) * 32 + lane;
-            const bool ok = !VF && w < wb && n < N;
+            const bool ok = w < wb && n < N;
             g[i] = ok ? P.state[3 * SN + (size_t)s * N + n] : (T)0;
             cg[i] = A::mul(P.c_g, ok ? P.par[6 * (size_t)N + n] : (T)0);
             gconv = gconv && (A::muladd(P.s_g, g[i], cg[i]) == g[i]);
@@ -725,8 +959,6 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             out_row = ordered ? (P.out + (size_t)s * P.out_stride) : (P.out + ((size_t)cta * P.S + s) * (size_t)L);   // tree mode: one partial row per CTA
         const T* carry = (ordered && first && head && !has_in && P.carry_in) ? P.carry_in + (size_t)s * P.carry_stride : nullptr;
         const int dist = P.dist;
-        // every RU warp this S warp serves is a full group of 32 filters (and there is at least one)
-        const bool fast_rows = wa < wb && (w_first + wb) * 32 <= N;
         int yb = 0;
         unsigned ypar = 0;
         long long pf_in = 0, pf_y = 0, pf_mix = 0, pf_out = 0;
@@ -738,70 +970,6 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
             const int pb = k % PD;
             const unsigned ppar = (unsigned)((k / PD) & 1);
             long long pc0 = HG_PROF_ON(P) ? clock64() : 0, pc1;
-            if (VF && sizeof(T) == 4 && GPS == 2 && fast_rows && !dist) {
-                // Steady state of the VF tiles (float): fetch the terms of both RU warps into registers and give the tile
-                // slots back BEFORE waiting for the running row — the RU warps are then never held up by the chain's
-                // latency, and the chain's stage is nothing but the hand-over and the 64-deep FADD chain.
-                float v0[32], v1[32];
-                const bool two = wa + 1 < wb;
-                mbar_wait(&y_full[wa * NB + yb], ypar);
-                {
-                    const float* vr = reinterpret_cast<const float*>(ytiles) + ((size_t)wa * NB + yb) * 32 * RS + lane * RS;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) ld4<float>(vr + 4 * q, *reinterpret_cast<float(*)[4]>(&v0[4 * q]));
-                }
-                if (two) {
-                    mbar_wait(&y_full[(wa + 1) * NB + yb], ypar);
-                    const float* vr = reinterpret_cast<const float*>(ytiles) + ((size_t)(wa + 1) * NB + yb) * 32 * RS + lane * RS;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) ld4<float>(vr + 4 * q, *reinterpret_cast<float(*)[4]>(&v1[4 * q]));
-                }
-                // the slots are free once every lane's loads have returned (the empty asm makes the arrive wait for them)
-                asm volatile("" ::"f"(v0[31]), "f"(two ? v1[31] : v0[30]) : "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&y_empty[wa * NB + yb]);
-                    if (two) mbar_arrive(&y_empty[(wa + 1) * NB + yb]);
-                }
-                if (HG_PROF_ON(P)) { pc1 = clock64(); pf_y += pc1 - pc0; pc0 = pc1; }
-                float a = 0.f;
-                if (summing) {
-                    if (smem_in) {
-                        mbar_wait(&ps_full[in_link * PD + pb], ppar);
-                        a = reinterpret_cast<const float*>(psum)[((size_t)in_link * PD + pb) * 32 + lane];
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&ps_empty[in_link * PD + pb]);
-                    } else if (carry) {
-                        if (lane < tn) a = (float)carry[tg + lane];
-                    }
-                    if (HG_PROF_ON(P)) { pc1 = clock64(); pf_in += pc1 - pc0; pc0 = pc1; }
-#pragma unroll
-                    for (int l = 0; l < 32; l++) a = __fadd_rn(v0[l], a);                  // filterbank.h:130, index order
-                    if (two) {
-#pragma unroll
-                        for (int l = 0; l < 32; l++) a = __fadd_rn(v1[l], a);
-                    }
-                    if (HG_PROF_ON(P)) { pc1 = clock64(); pf_mix += pc1 - pc0; pc0 = pc1; }
-                    if (!last) {
-                        mbar_wait(&ps_empty[sidx * PD + pb], ppar ^ 1u);
-                        reinterpret_cast<float*>(psum)[((size_t)sidx * PD + pb) * 32 + lane] = a;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&ps_full[sidx * PD + pb]);
-                    } else if (pout.on()) {
-                        pout.reserve(C, tg + TILE);
-                        T a1v[1] = {(T)a};
-                        pout.send(C, tg + lane, a1v);
-                    } else if (out_row) {
-                        if (lane < tn) {
-                            if (P.epi.kind && ordered) a = (float)epilogue_dev<T>(P.epi, (T)a, P.dry_in[(size_t)s * P.in_stride + tg + lane]);
-                            out_row[tg + lane] = (T)a;
-                        }
-                    }
-                    if (HG_PROF_ON(P)) pf_out += clock64() - pc0;
-                }
-                if (++yb == NB) { yb = 0; ypar ^= 1u; }
-                continue;
-            }
             if (summing) {
                 if (smem_in) {
                     // running row after the filters before this S warp's (left by S warp sidx-1, or by the gateway)
@@ -823,26 +991,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 const int rows = min(32, N - (w_first + w) * 32);
                 // acc = fl(fl(y_l[t] * g_l[t]) + acc) (fused in fma mode), l ascending: src/filterbank.h:130 — the same
                 // function of (y, g) whether the gains still move or not
-                if (VF) {
-                    // the tile holds the terms v_l[t], sample-major: this lane's 32 terms are one 128-byte row.  Lanes
-                    // past the bank's last filter wrote +0 terms (coefficients, state and gains are zero there).
-                    const T* vr = ytiles + ((size_t)w * NB + yb) * 32 * RS + lane * RS;
-                    if (dist) {
-                        for (int l = 0; l < rows; l++) acc = A::add(acc, softclip_dev<T>(vr[l]));                                 // :137
-                    } else if (rows == 32) {
-                        constexpr int CH = sizeof(T) == 4 ? 32 : 16;      // terms fetched per batch (registers)
-#pragma unroll
-                        for (int c0 = 0; c0 < 32; c0 += CH) {
-                            T v[CH];
-#pragma unroll
-                            for (int q = 0; q < CH / 4; q++) ld4<T>(vr + c0 + 4 * q, *reinterpret_cast<T(*)[4]>(&v[4 * q]));
-#pragma unroll
-                            for (int l = 0; l < CH; l++) acc = A::add(v[l], acc);
-                        }
-                    } else {
-                        for (int l = 0; l < rows; l++) acc = A::add(vr[l], acc);
-                    }
-                } else if (!gconv) {
+                if (!gconv) {
                     T gi = (T)0, cgi = (T)0;
 #pragma unroll
                     for (int j = 0; j < GPS; j++) if (j == i) { gi = g[j]; cgi = cg[j]; }
@@ -911,7 +1060,7 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
         for (int i = 0; i < GPS; i++) {
             const int w = wa + i;
             const int n = (w_first + w) * 32 + lane;
-            if (!VF && w < wb && n < N) P.state[3 * SN + (size_t)s * N + n] = g[i];
+            if (w < wb && n < N) P.state[3 * SN + (size_t)s * N + n] = g[i];
         }
         if (HG_PROF_ON(P) && lane == 0 && sidx == (NS > 1 ? 1 : 0)) {       // a middle S warp (inbound from shared memory)
             long long* q = P.prof + ((size_t)s * gridDim.x + cta) * 8;
@@ -923,17 +1072,20 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
 // pick RU warps per CTA (and 1 or 2 CTAs per SM, as shared memory allows) so that the CTAs fill whole
 // waves: each CTA runs the whole block, so a nearly empty last wave costs a full pass
 template <typename T>
-void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
+void fb_ru_config(const hg_fb* fb, bool bands, int* W_out, int* NS_out, int* cps_out) {
     const int groups = (fb->N + 31) / 32;
+    const bool vf = fb->arith != HG_ARITH_FMA && !bands && !(fb->cur_env && fb->env_mode != 2);     // TermTiles of the kernel that will run
     const int w_max = (fb->cur_env && fb->env_mode != 2) ? ru::W_MAX_ENV : ru::W_MAX;
     const size_t smem_sm = (size_t)227 * 1024;
-    int bestW = 4;
+    int bestW = 4, bestNS = vf ? ru::s_warps_vf(4, 1) : ru::s_warps(4);
     double best = -1;
     for (int per_sm = 1; per_sm <= 2; per_sm++) {
         for (int W = 4; W <= w_max; W++) {
-            if ((ru::Layout<T>(W, fb->env_mode == 2 && fb->cur_env).bytes() + 1024) * per_sm > smem_sm) continue;
+            const int NS = vf ? ru::s_warps_vf(W, per_sm) : ru::s_warps(W);
+            if (NS < (vf ? ru::NB_VF : 1)) continue;         // term tiles: one hand-over barrier pair per S warp, at least one per tile slot
+            if ((ru::Layout<T>(W, NS, fb->env_mode == 2 && fb->cur_env, vf).bytes() + 1024) * per_sm > smem_sm) continue;
             // registers: 80 per thread (launch bounds), W RU warps + their S warps + the gateway
-            if ((long)(W + ru::s_warps(W) + 1) * 32 * 80 * per_sm > 65536) continue;
+            if ((long)(W + NS + 1) * 32 * 80 * per_sm > 65536) continue;
             const long slots = (long)fb->sm_count * per_sm;
             const long ctas = (long)((groups + W - 1) / W) * fb->S;
             const long waves = (ctas + slots - 1) / slots;
@@ -942,40 +1094,43 @@ void fb_ru_config(const hg_fb* fb, int* W_out, int* cps_out) {
             const double fill = (double)groups * fb->S / ((double)waves * slots * W);
             const double busy = (double)(W * per_sm) / 16.0;
             const double eff = fill * (busy > 1.0 ? 1.0 : busy);
-            if (eff > best + 1e-9) { best = eff; bestW = W; }
+            if (eff > best + 1e-9) { best = eff; bestW = W; bestNS = NS; }
         }
     }
     *W_out = bestW;
+    *NS_out = bestNS;
     *cps_out = (groups + bestW - 1) / bestW;
 }
-template void fb_ru_config<float>(const hg_fb*, int*, int*);
-template void fb_ru_config<double>(const hg_fb*, int*, int*);
+template void fb_ru_config<float>(const hg_fb*, bool, int*, int*, int*);
+template void fb_ru_config<double>(const hg_fb*, bool, int*, int*, int*);
 
 template <typename T, bool FMA, bool BANDS, int ENV>
 static hg_status launch_ru(const FbRuParams<T>& Q, cudaStream_t st) {
-    const size_t smem = ru::Layout<T>(Q.W, ENV == 2).bytes();
+    constexpr bool VF = ru::TermTiles<FMA, BANDS, ENV>::value;
+    const size_t smem = ru::Layout<T>(Q.W, Q.NS, ENV == 2, VF).bytes();
+    const int threads = (Q.W + Q.NS + 1) * 32;
     auto kern = fb_exact_ru_kernel<T, FMA, BANDS, ENV>;
     HG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (Q.k.chain.ordered && (Q.k.out || Q.k.chain.outbox)) {
         // every CTA of a stream's chain must be resident at once: one that has not started yet would stall its
         // predecessor for good once the link's ring is full
         int per_sm = 0, dev = 0, sms = 0;
-        HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (Q.W + ru::s_warps(Q.W) + 1) * 32, smem));
+        HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         HG_CUDA(cudaGetDevice(&dev));
         HG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if ((long)Q.cps > (long)per_sm * sms)
             return fail(HG_ERR_UNSUPPORTED, "ordered mixdown: %d filters of one stream need %d CTAs, this GPU holds %d at once — split the bank over GPUs (hg_fb_process_sharded) or select HG_SUM_TREE",
                         Q.k.N, Q.cps, per_sm * sms);
     }
-    kern<<<dim3(Q.cps, Q.k.S), (Q.W + ru::s_warps(Q.W) + 1) * 32, smem, st>>>(Q);
+    kern<<<dim3(Q.cps, Q.k.S), threads, smem, st>>>(Q);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
 
 template <typename T>
-hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int cps, cudaStream_t st, const FbEnvArgs<T>* env) {
+hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W, int NS, int cps, cudaStream_t st, const FbEnvArgs<T>* env) {
     FbRuParams<T> Q;
-    Q.k = P; Q.W = W; Q.cps = cps;
+    Q.k = P; Q.W = W; Q.NS = NS; Q.cps = cps;
     Q.env = nullptr; Q.rms_sum = nullptr; Q.rms_ring = nullptr; Q.width = 1; Q.hop = 1; Q.env_rows = 0; Q.t_base = 0; Q.tick0 = 0;
     Q.in_lag = nullptr; Q.lag_stride = 0; Q.lag_state = nullptr; Q.lag_par = nullptr; Q.lag_taps = 0;
     if (env) {
@@ -990,7 +1145,7 @@ hg_status fb_launch_exact_ru(bool fma, bool bands, const FbK1Params<T>& P, int W
     if (bands) return fma ? launch_ru<T, true, true, 0>(Q, st) : launch_ru<T, false, true, 0>(Q, st);
     return fma ? launch_ru<T, true, false, 0>(Q, st) : launch_ru<T, false, false, 0>(Q, st);
 }
-template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, cudaStream_t, const FbEnvArgs<float>*);
-template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, cudaStream_t, const FbEnvArgs<double>*);
+template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>&, int, int, int, cudaStream_t, const FbEnvArgs<float>*);
+template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, int, cudaStream_t, const FbEnvArgs<double>*);
 
 }  // namespace hg

@@ -37,3 +37,9 @@ print(info)
 for i, n in enumerate(names):
     col = buf[:, i].astype(np.float64)
     print(f"  {n:28s} per sample: mean {col.mean()/Ls:8.2f}  first {col[0]/Ls:8.2f}  mid {col[G//2]/Ls:8.2f}  last {col[-1]/Ls:8.2f}  max {col.max()/Ls:8.2f}")
+if os.environ.get("HG_PROF_TABLE"):
+    print("cta: " + " ".join(f"{n[:10]:>10s}" for n in names))
+    step = max(1, G // 40)
+    rows = sorted(set(list(range(0, G, step)) + list(range(max(0, G // 2 - 12), min(G, G // 2 + 12)))))
+    for c in rows:
+        print(f"{c:4d} " + " ".join(f"{buf[c, i] / Ls:10.2f}" for i in range(len(names))))
