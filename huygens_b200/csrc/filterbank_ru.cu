@@ -66,8 +66,7 @@ __host__ __device__ constexpr int s_warps(int W) { return (W + GPS - 1) / GPS; }
 constexpr int CTA_WARPS_MAX = 24;   // 24 warps x 32 lanes x 80 registers fit the 65 536 of an SM (ptxas grants 25 warps only 72)
 __host__ __device__ constexpr int s_warps_vf(int W, int per_sm) {
     const int room = CTA_WARPS_MAX / per_sm - W - 1;
-    const int cap = W < HG_RU_NS_CAP ? W : HG_RU_NS_CAP;
-    return room < cap ? room : cap;
+    return room < HG_RU_NS_CAP ? room : HG_RU_NS_CAP;
 }
 // which kernels keep the mixdown TERMS fl(y*g) in their tiles (the ring followers read y back; fma needs y and g)
 template <bool FMA, bool BANDS, int ENV> struct TermTiles { static constexpr bool value = !FMA && !BANDS && ENV != 1; };
@@ -403,34 +402,29 @@ fb_exact_ru_kernel(FbRuParams<T> Q) {
                 c++;
                 progress = true;
             }
-            // Gateway: up to GD tiles are accepted per pass, and every packet of the window that has not arrived is
-            // polled again in the same pass — a poll is an L2 round trip (1-2 k cycles under load), so a gateway that
-            // asked for one tile per round trip would cap the whole chain at a tile per round trip.
-#pragma unroll
-            for (int rep = 0; rep < GD; rep++) {
-                const int pb = gk % PD;
-                if (!(gk < gtiles && mbar_poll(&gempty[pb], (unsigned)(((gk / PD) & 1) ^ 1)))) break;
+            const int pb = gk % PD;
+            if (gk < gtiles && mbar_poll(&gempty[pb], (unsigned)(((gk / PD) & 1) ^ 1))) {
                 const long t = (long)gk * TILE + lane;
                 const bool got = !(t < L) || pin.ready(C, t, rq[0]);
-                if (!__all_sync(0xffffffffu, got)) break;
-                T v[1];
-                memcpy(v, rq[0].w, sizeof(v));
-                gslot[pb * 32 + lane] = v[0];
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&gfull[pb]);
-                    pin.release(C, (long)(gk + 1) * TILE);       // the packet is in shared memory: its ring slot is free
+                if (__all_sync(0xffffffffu, got)) {
+                    T v[1];
+                    memcpy(v, rq[0].w, sizeof(v));
+                    gslot[pb * 32 + lane] = v[0];
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&gfull[pb]);
+                        pin.release(C, (long)(gk + 1) * TILE);       // the packet is in shared memory: its ring slot is free
+                    }
+                    gk++;
+#pragma unroll
+                    for (int i = 0; i + 1 < GD; i++) rq[i] = rq[i + 1];
+                    if (gk + GD - 1 < gtiles && (long)(gk + GD - 1) * TILE + lane < L) pin.issue(C, (long)(gk + GD - 1) * TILE + lane, rq[GD - 1]);
+                    progress = true;
+                } else if (!got) {
+                    // poll again (this lane's packet only).  More polls in flight do not help: strong loads of one warp do
+                    // not overlap, so a gateway takes at most one tile per L2 round trip (measured: deeper windows are slower)
+                    pin.issue(C, t, rq[0]);
                 }
-                gk++;
-#pragma unroll
-                for (int i = 0; i + 1 < GD; i++) rq[i] = rq[i + 1];
-                if (gk + GD - 1 < gtiles && (long)(gk + GD - 1) * TILE + lane < L) pin.issue(C, (long)(gk + GD - 1) * TILE + lane, rq[GD - 1]);
-                progress = true;
-            }
-#pragma unroll
-            for (int i = 0; i < GD; i++) {                       // poll again what is still missing (this lane's packets only)
-                const long t = (long)(gk + i) * TILE + lane;
-                if (gk + i < gtiles && t < L && !(progress && i == GD - 1) && !pin.ready(C, t, rq[i])) pin.issue(C, t, rq[i]);
             }
             if (progress) spins = 0;
             else {
