@@ -166,14 +166,21 @@ __global__ void __launch_bounds__(512) kb(float* sink, int ntiles, long long* cl
         const long long c0 = clock64();
 #pragma unroll 1
         for (int kt = 0; kt < ntiles; kt++) {
-            if (MODE == 0) mbar_wait(&empty[warp][yb], par ^ 1u);
-            else if (!ready) mbar_wait(&empty[warp][yb], par ^ 1u);
+            // MODE 2: no wait at all (consumer idle); 3: wait only, never signal; 4: signal without __syncwarp; 5: hand-over every
+            // second tile (two tiles per slot pair)
+            if (MODE == 0 || MODE == 3 || MODE == 4) mbar_wait(&empty[warp][yb], par ^ 1u);
+            else if (MODE == 1 && !ready) mbar_wait(&empty[warp][yb], par ^ 1u);
+            else if (MODE == 5 && !(kt & 1)) mbar_wait(&empty[warp][yb], par ^ 1u);
             const int nyb = yb ^ 1; const unsigned npar = par ^ (unsigned)yb;
             if (MODE == 1) ready = mbar_poll(&empty[warp][nyb], npar ^ 1u);
-            tile_v0(xs + (kt & 31) * TILE, vbase + yb * TILE * VS, b0, a1, a2, p, g, s);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[warp][yb]);
-            yb = nyb; par = npar;
+            tile_v0(xs + (kt & 31) * TILE, vbase + (MODE == 5 ? (kt & 1) : yb) * TILE * VS, b0, a1, a2, p, g, s);
+            if (MODE != 4 && MODE != 3) __syncwarp();
+            if (MODE == 5) { if (kt & 1) { if (lane == 0) mbar_arrive(&full[warp][yb]); yb = nyb; par = npar; } }
+            else {
+                if (MODE != 3 && lane == 0) mbar_arrive(&full[warp][yb]);
+                if (MODE == 3 && lane == 0) mbar_arrive(&empty[warp][yb]);       // keep our own wait satisfied
+                yb = nyb; par = npar;
+            }
         }
         const long long c1 = clock64();
         if (s.y1 == 123456.f) sink[0] = s.y1 + s.t2;
@@ -182,7 +189,8 @@ __global__ void __launch_bounds__(512) kb(float* sink, int ntiles, long long* cl
         const int w = warp - 4 - consumer_shift;
         int yb = 0; unsigned par = 0;
         float acc = 0.f;
-        for (int kt = 0; kt < ntiles; kt++) {
+        const int nt = (MODE == 5) ? ntiles / 2 : ((MODE == 2 || MODE == 3) ? 0 : ntiles);
+        for (int kt = 0; kt < nt; kt++) {
             mbar_wait(&full[w][yb], par);
             acc += tiles[w][yb][lane * VS];
             __syncwarp();
@@ -202,6 +210,59 @@ void runb(const char* name, int producers, int shift) {
     long long h[16];
     cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
     printf("%-60s producers %d: %6.2f cycles per sample  (%s)\n", name, producers, (double)h[0] / (ntiles * 32.0), cudaGetErrorString(e));
+    cudaFree(sink); cudaFree(clk);
+}
+
+// ring of NBS slots between the producer and its consumer (MODE 0 protocol): how deep must it be to hide the hand-over's round trip?
+template <int NBS, bool SPIN>
+__global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* clk) {
+    __shared__ __align__(16) float xs[1024];
+    __shared__ __align__(16) float tiles[NBS][TILE * VS];
+    __shared__ unsigned long long full[NBS], empty[NBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = sinf(0.37f * i) * 0.5f;
+    if (threadIdx.x == 0) for (int b = 0; b < NBS; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], 1); }
+    __syncthreads();
+    if (warp == 0) {
+        const float w = 0.01f + 0.002f * lane, r = 0.999f;
+        const float a1 = -2.f * r * cosf(w), a2 = r * r, b0 = 0.01f, p = 1.0f, g = 0.5f;
+        St s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int yb = 0; unsigned par = 0;
+        const long long c0 = clock64();
+#pragma unroll 1
+        for (int kt = 0; kt < ntiles; kt++) {
+            if (SPIN) { while (!mbar_poll(&empty[yb], par ^ 1u)) {} } else mbar_wait(&empty[yb], par ^ 1u);
+            tile_v0(xs + (kt & 31) * TILE, &tiles[yb][0] + lane, b0, a1, a2, p, g, s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[yb]);
+            if (++yb == NBS) { yb = 0; par ^= 1u; }
+        }
+        const long long c1 = clock64();
+        if (s.y1 == 123456.f) sink[0] = s.y1 + s.t2;
+        if (lane == 0) clk[0] = c1 - c0;
+    } else if (warp == 5) {
+        int yb = 0; unsigned par = 0;
+        float acc = 0.f;
+        for (int kt = 0; kt < ntiles; kt++) {
+            if (SPIN) { while (!mbar_poll(&full[yb], par)) {} } else mbar_wait(&full[yb], par);
+            acc += tiles[yb][lane * VS];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[yb]);
+            if (++yb == NBS) { yb = 0; par ^= 1u; }
+        }
+        if (acc == 123456.f) sink[0] = acc;
+    }
+}
+template <int NBS, bool SPIN>
+void rund(const char* name) {
+    float* sink; long long* clk;
+    cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
+    const int ntiles = 20000;
+    for (int rep = 0; rep < 2; rep++) { kd<NBS, SPIN><<<1, 8 * 32>>>(sink, ntiles, clk); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError();
+    long long h[16];
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-60s %6.2f cycles per sample  (%s)\n", name, (double)h[0] / (ntiles * 32.0), cudaGetErrorString(e));
     cudaFree(sink); cudaFree(clk);
 }
 
@@ -235,7 +296,17 @@ int main() {
     runb<0>("hand-over per tile, consumer on the next scheduler", 1, 1);
     runb<1>("next slot probed before the tile, consumer same scheduler", 1, 0);
     runb<1>("next slot probed before the tile, consumer next scheduler", 1, 1);
+    runb<2>("signal only (consumer idle, never waits)", 1, 1);
+    runb<3>("wait only (self-satisfied), no syncwarp", 1, 1);
+    runb<4>("hand-over per tile without __syncwarp", 1, 1);
+    runb<5>("hand-over every second tile", 1, 1);
     runb<0>("hand-over per tile, 4 producers + 4 consumers", 4, 0);
     runb<1>("next slot probed before the tile, 4 producers + 4 consumers", 4, 0);
+    rund<2, false>("ring of 2 slots, try_wait");
+    rund<3, false>("ring of 3 slots, try_wait");
+    rund<4, false>("ring of 4 slots, try_wait");
+    rund<6, false>("ring of 6 slots, try_wait");
+    rund<2, true>("ring of 2 slots, test_wait spin");
+    rund<4, true>("ring of 4 slots, test_wait spin");
     return 0;
 }
