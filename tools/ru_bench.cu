@@ -145,6 +145,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_hint(unsigned long long* b, unsigned parity, unsigned ns) {
+    unsigned ok = 0;
+    while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"(ns) : "memory");
+}
 // MODE 0: wait / render / arrive as in the kernel.  MODE 1: the next slot's barrier is probed before this tile is rendered.
 // The consumer warp (warp 4 + producer index, on the producer's scheduler when SAME, else the next one) frees the slot at once.
 template <int MODE>
@@ -214,7 +218,7 @@ void runb(const char* name, int producers, int shift) {
 }
 
 // ring of NBS slots between the producer and its consumer (MODE 0 protocol): how deep must it be to hide the hand-over's round trip?
-template <int NBS, bool SPIN>
+template <int NBS, int SPIN>
 __global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* clk) {
     __shared__ __align__(16) float xs[1024];
     __shared__ __align__(16) float tiles[NBS][TILE * VS];
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* cl
         const long long c0 = clock64();
 #pragma unroll 1
         for (int kt = 0; kt < ntiles; kt++) {
-            if (SPIN) { while (!mbar_poll(&empty[yb], par ^ 1u)) {} } else mbar_wait(&empty[yb], par ^ 1u);
+            if (SPIN == 1) { while (!mbar_poll(&empty[yb], par ^ 1u)) {} } else if (SPIN == 3) mbar_wait_hint(&empty[yb], par ^ 1u, 10000000u); else mbar_wait(&empty[yb], par ^ 1u);
             tile_v0(xs + (kt & 31) * TILE, &tiles[yb][0] + lane, b0, a1, a2, p, g, s);
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[yb]);
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* cl
         int yb = 0; unsigned par = 0;
         float acc = 0.f;
         for (int kt = 0; kt < ntiles; kt++) {
-            if (SPIN) { while (!mbar_poll(&full[yb], par)) {} } else mbar_wait(&full[yb], par);
+            if (SPIN == 1) { while (!mbar_poll(&full[yb], par)) {} } else if (SPIN >= 2 && SPIN <= 3) mbar_wait_hint(&full[yb], par, 10000000u); else if (SPIN == 4) { while (!mbar_poll(&full[yb], par)) __nanosleep(200); } else mbar_wait(&full[yb], par);
             acc += tiles[yb][lane * VS];
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[yb]);
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* cl
         if (acc == 123456.f) sink[0] = acc;
     }
 }
-template <int NBS, bool SPIN>
+template <int NBS, int SPIN>
 void rund(const char* name) {
     float* sink; long long* clk;
     cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
@@ -302,11 +306,16 @@ int main() {
     runb<5>("hand-over every second tile", 1, 1);
     runb<0>("hand-over per tile, 4 producers + 4 consumers", 4, 0);
     runb<1>("next slot probed before the tile, 4 producers + 4 consumers", 4, 0);
-    rund<2, false>("ring of 2 slots, try_wait");
-    rund<3, false>("ring of 3 slots, try_wait");
-    rund<4, false>("ring of 4 slots, try_wait");
-    rund<6, false>("ring of 6 slots, try_wait");
-    rund<2, true>("ring of 2 slots, test_wait spin");
-    rund<4, true>("ring of 4 slots, test_wait spin");
+    rund<2, 0>("ring of 2 slots, try_wait");
+    rund<3, 0>("ring of 3 slots, try_wait");
+    rund<4, 0>("ring of 4 slots, try_wait");
+    rund<6, 0>("ring of 6 slots, try_wait");
+    rund<2, 1>("ring of 2 slots, test_wait spin");
+    rund<4, 1>("ring of 4 slots, test_wait spin");
+    rund<2, 2>("ring of 2 slots, consumer waits with a 10 ms suspend hint");
+    rund<4, 2>("ring of 4 slots, consumer waits with a 10 ms suspend hint");
+    rund<2, 3>("ring of 2 slots, both wait with a 10 ms suspend hint");
+    rund<4, 3>("ring of 4 slots, both wait with a 10 ms suspend hint");
+    rund<4, 4>("ring of 4 slots, consumer polls with 200 ns naps");
     return 0;
 }
