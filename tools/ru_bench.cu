@@ -247,14 +247,18 @@ __global__ void __launch_bounds__(512) kd(float* sink, int ntiles, long long* cl
     } else if (warp == 5) {
         int yb = 0; unsigned par = 0;
         float acc = 0.f;
+        long long tw = 0, tt0 = clock64();
         for (int kt = 0; kt < ntiles; kt++) {
+            const long long q0 = clock64();
             if (SPIN == 1) { while (!mbar_poll(&full[yb], par)) {} } else if (SPIN >= 2 && SPIN <= 3) mbar_wait_hint(&full[yb], par, 10000000u); else if (SPIN == 4) { while (!mbar_poll(&full[yb], par)) __nanosleep(200); } else mbar_wait(&full[yb], par);
+            tw += clock64() - q0;
             acc += tiles[yb][lane * VS];
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[yb]);
             if (++yb == NBS) { yb = 0; par ^= 1u; }
         }
         if (acc == 123456.f) sink[0] = acc;
+        if (lane == 0) { clk[1] = tw; clk[2] = clock64() - tt0; }
     }
 }
 template <int NBS, int SPIN>
@@ -263,6 +267,66 @@ void rund(const char* name) {
     cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
     const int ntiles = 20000;
     for (int rep = 0; rep < 2; rep++) { kd<NBS, SPIN><<<1, 8 * 32>>>(sink, ntiles, clk); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError();
+    long long h[16];
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-60s %6.2f cycles per sample; consumer: %7.1f cycles per tile, of which %7.1f in the wait  (%s)\n", name, (double)h[0] / (ntiles * 32.0), (double)h[2] / ntiles, (double)h[1] / ntiles, cudaGetErrorString(e));
+    cudaFree(sink); cudaFree(clk);
+}
+
+// the slot wait through a plain shared-memory flag instead of an mbarrier: the consumer stores the number of tiles it has taken
+// (st.volatile.shared after its reads), the producer loads it a tile ahead (ld.volatile.shared: an ordinary scoreboarded load)
+template <int NBS>
+__global__ void __launch_bounds__(512) kf(float* sink, int ntiles, long long* clk) {
+    __shared__ __align__(16) float xs[1024];
+    __shared__ __align__(16) float tiles[NBS][TILE * VS];
+    __shared__ unsigned long long full[NBS];
+    __shared__ volatile int taken;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = sinf(0.37f * i) * 0.5f;
+    if (threadIdx.x == 0) { for (int b = 0; b < NBS; b++) mbar_init(&full[b], 1); taken = 0; }
+    __syncthreads();
+    if (warp == 0) {
+        const float w = 0.01f + 0.002f * lane, r = 0.999f;
+        const float a1 = -2.f * r * cosf(w), a2 = r * r, b0 = 0.01f, p = 1.0f, g = 0.5f;
+        St s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int yb = 0;
+        int seen = taken;                       // tiles the consumer has taken, as of the last look
+        const long long c0 = clock64();
+#pragma unroll 1
+        for (int kt = 0; kt < ntiles; kt++) {
+            while (kt - seen >= NBS) seen = taken;          // slot of tile kt - NBS not yet taken: look again
+            const int look = taken;                          // a look ahead for the next tile, lands during this one
+            tile_v0(xs + (kt & 31) * TILE, &tiles[yb][0] + lane, b0, a1, a2, p, g, s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[yb]);
+            seen = look;
+            if (++yb == NBS) yb = 0;
+        }
+        const long long c1 = clock64();
+        if (s.y1 == 123456.f) sink[0] = s.y1 + s.t2;
+        if (lane == 0) clk[0] = c1 - c0;
+    } else if (warp == 5) {
+        int yb = 0; unsigned par = 0;
+        float acc = 0.f;
+        for (int kt = 0; kt < ntiles; kt++) {
+            mbar_wait(&full[yb], par);
+            const float v = tiles[yb][lane * VS];
+            acc += v;
+            asm volatile("" ::"f"(v) : "memory");            // the load has returned
+            __syncwarp();
+            if (lane == 0) taken = kt + 1;
+            if (++yb == NBS) { yb = 0; par ^= 1u; }
+        }
+        if (acc == 123456.f) sink[0] = acc;
+    }
+}
+template <int NBS>
+void runf(const char* name) {
+    float* sink; long long* clk;
+    cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
+    const int ntiles = 20000;
+    for (int rep = 0; rep < 2; rep++) { kf<NBS><<<1, 8 * 32>>>(sink, ntiles, clk); cudaDeviceSynchronize(); }
     cudaError_t e = cudaGetLastError();
     long long h[16];
     cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
@@ -317,5 +381,7 @@ int main() {
     rund<2, 3>("ring of 2 slots, both wait with a 10 ms suspend hint");
     rund<4, 3>("ring of 4 slots, both wait with a 10 ms suspend hint");
     rund<4, 4>("ring of 4 slots, consumer polls with 200 ns naps");
+    runf<2>("ring of 2 slots, slot wait = shared-memory counter read a tile ahead");
+    runf<4>("ring of 4 slots, slot wait = shared-memory counter read a tile ahead");
     return 0;
 }
