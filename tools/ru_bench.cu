@@ -334,6 +334,121 @@ void runf(const char* name) {
     cudaFree(sink); cudaFree(clk);
 }
 
+// which part of the interaction costs the producer?  PW: producer waits on `empty`; CW: consumer waits on `full`;
+// CL: consumer loads from the tile; CA: consumer arrives on `empty`
+template <bool PW, bool CW, bool CL, bool CA>
+__global__ void __launch_bounds__(512) ke(float* sink, int ntiles, long long* clk) {
+    constexpr int NBS = 4;
+    __shared__ __align__(16) float xs[1024];
+    __shared__ __align__(16) float tiles[NBS][TILE * VS];
+    __shared__ unsigned long long full[NBS], empty[NBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = sinf(0.37f * i) * 0.5f;
+    if (threadIdx.x == 0) for (int b = 0; b < NBS; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], 1); }
+    __syncthreads();
+    if (warp == 0) {
+        const float w = 0.01f + 0.002f * lane, r = 0.999f;
+        const float a1 = -2.f * r * cosf(w), a2 = r * r, b0 = 0.01f, p = 1.0f, g = 0.5f;
+        St s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int yb = 0; unsigned par = 0;
+        const long long c0 = clock64();
+#pragma unroll 1
+        for (int kt = 0; kt < ntiles; kt++) {
+            if (PW) mbar_wait(&empty[yb], par ^ 1u);
+            tile_v0(xs + (kt & 31) * TILE, &tiles[yb][0] + lane, b0, a1, a2, p, g, s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[yb]);
+            if (++yb == NBS) { yb = 0; par ^= 1u; }
+        }
+        const long long c1 = clock64();
+        if (s.y1 == 123456.f) sink[0] = s.y1 + s.t2;
+        if (lane == 0) clk[0] = c1 - c0;
+    } else if (warp == 5) {
+        int yb = 0; unsigned par = 0;
+        float acc = 0.f;
+        for (int kt = 0; kt < ntiles; kt++) {
+            if (CW) mbar_wait(&full[yb], par); else __nanosleep(250);
+            if (CL) acc += tiles[yb][lane * VS];
+            __syncwarp();
+            if (CA && lane == 0) mbar_arrive(&empty[yb]);
+            if (++yb == NBS) { yb = 0; par ^= 1u; }
+        }
+        if (acc == 123456.f) sink[0] = acc;
+    }
+}
+template <bool PW, bool CW, bool CL, bool CA>
+void rune(const char* name) {
+    float* sink; long long* clk;
+    cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
+    const int ntiles = 20000;
+    for (int rep = 0; rep < 2; rep++) { ke<PW, CW, CL, CA><<<1, 8 * 32>>>(sink, ntiles, clk); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError();
+    long long h[16];
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-76s %6.2f cycles per sample  (%s)\n", name, (double)h[0] / (ntiles * 32.0), cudaGetErrorString(e));
+    cudaFree(sink); cudaFree(clk);
+}
+
+// what does another warp's shared-memory reading cost the producer?  No barriers; the reader does NL loads of width 4 or 16 bytes
+// every `nap` ns from the tile slots (WHERE 0), from the input ring the producer also reads (1), or from a region nobody else touches (2)
+template <int NL, bool WIDE, int WHERE>
+__global__ void __launch_bounds__(512) kl(float* sink, int ntiles, long long* clk, unsigned nap) {
+    __shared__ __align__(16) float xs[1024];
+    __shared__ __align__(16) float tiles[4][TILE * VS];
+    __shared__ __align__(16) float other[4][TILE * VS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = sinf(0.37f * i) * 0.5f;
+    for (int i = threadIdx.x; i < 4 * TILE * VS; i += blockDim.x) { (&other[0][0])[i] = 1.f; (&tiles[0][0])[i] = 0.f; }
+    __shared__ volatile int done;
+    if (threadIdx.x == 0) done = 0;
+    __syncthreads();
+    if (warp == 0) {
+        const float w = 0.01f + 0.002f * lane, r = 0.999f;
+        const float a1 = -2.f * r * cosf(w), a2 = r * r, b0 = 0.01f, p = 1.0f, g = 0.5f;
+        St s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int yb = 0;
+        const long long c0 = clock64();
+#pragma unroll 1
+        for (int kt = 0; kt < ntiles; kt++) {
+            tile_v0(xs + (kt & 31) * TILE, &tiles[yb][0] + lane, b0, a1, a2, p, g, s);
+            if (++yb == 4) yb = 0;
+        }
+        const long long c1 = clock64();
+        if (s.y1 == 123456.f) sink[0] = s.y1 + s.t2;
+        if (lane == 0) { clk[0] = c1 - c0; done = 1; }
+    } else if (warp == 5) {
+        float acc = 0.f;
+        int yb = 0;
+        long long n = 0;
+        while (!done) {
+            const float* base = WHERE == 0 ? &tiles[yb][0] : (WHERE == 1 ? xs : &other[yb][0]);
+            const float* row = WHERE == 1 ? base + (lane & 7) * 32 : base + lane * VS;
+#pragma unroll
+            for (int i = 0; i < NL; i++) {
+                if (WIDE) { const float4 v = *reinterpret_cast<const float4*>(row + 4 * i); acc += v.x + v.w; }
+                else acc += *reinterpret_cast<const volatile float*>(row + i);
+            }
+            if (++yb == 4) yb = 0;
+            n++;
+            if (nap) __nanosleep(nap);
+        }
+        if (acc == 123456.f) sink[0] = acc;
+        if (lane == 0) clk[1] = n;
+    }
+}
+template <int NL, bool WIDE, int WHERE>
+void runl(const char* name, unsigned nap) {
+    float* sink; long long* clk;
+    cudaMalloc(&sink, 4); cudaMalloc(&clk, 16 * 8);
+    const int ntiles = 20000;
+    for (int rep = 0; rep < 2; rep++) { kl<NL, WIDE, WHERE><<<1, 8 * 32>>>(sink, ntiles, clk, nap); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError();
+    long long h[16];
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-70s %6.2f cycles per sample, %5.2f reader passes per tile  (%s)\n", name, (double)h[0] / (ntiles * 32.0), (double)h[1] / ntiles, cudaGetErrorString(e));
+    cudaFree(sink); cudaFree(clk);
+}
+
 template <int VAR>
 void run(const char* name, int warps, int stride) {
     float* sink; long long* clk;
@@ -383,5 +498,19 @@ int main() {
     rund<4, 4>("ring of 4 slots, consumer polls with 200 ns naps");
     runf<2>("ring of 2 slots, slot wait = shared-memory counter read a tile ahead");
     runf<4>("ring of 4 slots, slot wait = shared-memory counter read a tile ahead");
+    rune<false, true, false, false>("consumer only waits on the tile signal (no load, no release); producer never waits");
+    rune<false, true, true, false>("consumer waits and loads; producer never waits");
+    rune<false, true, true, true>("consumer waits, loads, releases; producer never waits");
+    rune<true, true, false, true>("full protocol without the consumer's load");
+    rune<true, true, true, true>("full protocol");
+    rune<false, false, true, false>("consumer only loads from the tiles every 250 ns (no barriers)");
+    runl<1, false, 0>("reader: 1 LDS from the tile slots every 250 ns", 250);
+    runl<1, false, 2>("reader: 1 LDS from an untouched region every 250 ns", 250);
+    runl<1, false, 1>("reader: 1 LDS from the input ring every 250 ns", 250);
+    runl<8, true, 0>("reader: 8 LDS.128 from the tile slots every 250 ns", 250);
+    runl<8, true, 2>("reader: 8 LDS.128 from an untouched region every 250 ns", 250);
+    runl<8, true, 0>("reader: 8 LDS.128 from the tile slots every 1000 ns", 1000);
+    runl<8, true, 0>("reader: 8 LDS.128 from the tile slots, no nap", 0);
+    runl<0, false, 2>("reader: no loads, naps of 250 ns only", 250);
     return 0;
 }
