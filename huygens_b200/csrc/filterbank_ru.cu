@@ -5,24 +5,28 @@
 // division of labour: with many warps per scheduler the 12-cycle dependency chain of one lane hides
 // behind the other warps, so the goal is the lowest instruction count per filter-sample, not the
 // shortest critical path.
-//     RU warps  lane = filter: feed-forward taps, pre-gain and the recurrence (x by LDS.128 broadcast,
-//               y out by STS.128 into a 2-deep ring of [32][TILE] tiles); own y1, y2 and p
-//     S warps   lane = sample: add the filters of their RU warps, in index order and with the reference's rounding
-//               (src/filterbank.h:130,137), onto the running bank-sum row: S warp i receives it from S warp i-1
-//               (shared memory), S warp 0 from the CTA of the filters before and the last S warp hands it to the
-//               next CTA (chain.cuh); the chain's tail writes out[t].  They own the mix gains g (replayed per
-//               sample while they still move) and stream per-band rows; S warp 0 also feeds the input ring by
-//               TMA bulk copies
-//     G warp    the chain's gateway: keeps the inbound packets of the next two tiles in flight and drops the running
-//               row into shared memory for S warp 0, so no S warp ever waits on an L2 round trip
-// Tile formats.  Strict arithmetic without per-band output or ring followers (VF): the RU warps also own the mix gains and
-// leave the mixdown TERMS v = fl(y*g) in the tile, sample-major [32 samples][32 filters]: an S warp fetches the 32
-// terms of its sample with 8 LDS.128 and its whole stage is the 32-deep FADD chain.  Otherwise the tile holds y,
-// filter-major, and the S warps own the gains (fused multiply-add, per-band rows, followers reading y back).
-// One CTA = W RU warps + ceil(W/2) S warps + the gateway, of one stream; full/empty mbarriers per RU warp, no __syncthreads
-// in the steady state, where an RU warp runs whole input chunks with nothing but the two hand-over barriers
-// per tile around the unrolled recurrence.  7.5 (taps {g,0,-g}) to 10.5 (general taps) RU instructions + ~3 S
-// instructions per filter-sample against 11 algorithmic issue slots (12.8 issued in total, ncu).
+//     RU warps  lane = filter: feed-forward taps, pre-gain and the recurrence (x by LDS.128 broadcast) into a 2-deep
+//               ring of 32-sample tiles; own y1, y2 and p
+//     S warps   lane = sample: add the CTA's filters, in index order and with the reference's rounding
+//               (src/filterbank.h:130,137), onto the running bank-sum row that comes from the CTA of the filters before
+//               and goes to the next CTA (chain.cuh); the chain's tail writes out[t]
+//     G warp    feeds the input ring by TMA bulk copies; gateway of the links that a single warp reads (a device's
+//               inbox, short chains, every link of the y-tile kernels): keeps the inbound packets of the next tiles in
+//               flight and drops the running row into shared memory
+// Tile formats.
+//   * Term tiles (strict arithmetic, no per-band rows, no ring followers): the RU warps also own the mix gains and leave
+//     the mixdown TERMS v = fl(y*g) in the tile, sample-major [32 samples][32 filters].  S warp j adds ALL the CTA's
+//     filters for the tiles k = j (mod NS), walking the RU warps' tiles of that index (terms fetched a batch ahead of the
+//     additions, slots given back as soon as their terms are in registers): the CTA is one stage of the chain, and on
+//     long chains the S warps poll the links themselves, one credit word per reading warp.  Hand-over barriers of an RU
+//     warp are per S warp (an mbarrier's phase bit only tells one phase ahead).
+//   * y tiles (fused multiply-add, per-band rows, ring followers reading y back): the tile holds y, filter-major;
+//     ceil(W/2) S warps own the gains (replayed per sample while they still move), stream the per-band rows and hand
+//     the running row to each other through shared memory; S warp 0 gets it from the gateway.
+// One CTA = W RU warps + NS S warps + G, of one stream; no __syncthreads in the steady state, where an RU warp runs whole
+// input chunks with nothing but the two hand-over barriers per tile around the unrolled recurrence.  9.75 (taps
+// {g,0,-g}) to 12.25 (general taps) RU instructions per filter-sample with term tiles, 13.4 issued in total on
+// BASELINE configs[2] (ncu) against 11 algorithmic issue slots.
 // ENV = 1 / 2 fuses one RMSbank envelope follower per band behind the filters: ring of y^2 in HBM, or a
 // lagged replica of every filter that regenerates y[t-width] bit for bit (see FbRuParams).
 #include "hg_common.cuh"
