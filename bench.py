@@ -695,7 +695,7 @@ def main():
         scan_info = {"value": float(N) * L / t_scan, "unit": "filter-samples/s", "ms_per_step": t_scan * 1e3,
                      "roofline_frac": float(N) * L / t_scan * SLOTS_PER_FILTER_SAMPLE / peak["slots_per_s"],
                      "max_abs_diff_vs_exact_rel_peak": diff,
-                     "note": "not bit-identical; measured error vs the oracle in profiles/scan_error_r1.json and DESIGN.md §5"}
+                     "note": "not bit-identical; measured error vs the oracle in profiles/scan_error_r2.json and DESIGN.md §5"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
