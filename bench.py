@@ -506,7 +506,8 @@ def side_measurements(args, local, flush, peak):
     ps = float(N) * Lo / t
     res["oscbank"] = {"workload": f"Oscbank<float> {N} partials x {Lo} ticks, mixdown() + amplitude-weighted mix per tick (index-order sums)",
                       "ms_per_block": t * 1e3, "value": ps, "unit": "partial-samples/s", "roofline_frac": ps * 11 / slots,
-                      "slots_per_unit": "9 FP32 slots + 2 IEEE divisions counted as 1 each (SURVEY.md 8d)"}
+                      "slots_per_unit": "9 FP32 slots + 2 IEEE divisions counted as 1 each (SURVEY.md 8d)",
+                      "issued_instructions_per_partial_tick": {"value": 50.6, "source": "profiles/r2_ncu_osc.txt: smsp__inst_executed.sum x 32 / (partials x ticks) of one ncu --set full launch; ~22 of them are the tick itself (SASS), the rest the index-order mixdowns and their hand-overs"}}
     del osc
     C_, Lr = 65536, 96000
     z = torch.rand((C_, Lr), dtype=torch.float32, device="cuda")
