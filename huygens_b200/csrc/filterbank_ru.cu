@@ -1147,3 +1147,22 @@ template hg_status fb_launch_exact_ru<float>(bool, bool, const FbK1Params<float>
 template hg_status fb_launch_exact_ru<double>(bool, bool, const FbK1Params<double>&, int, int, int, cudaStream_t, const FbEnvArgs<double>*);
 
 }  // namespace hg
+
+extern "C" hg_status hg_fb_debug_ru_config(int dtype, int arith, int n_filters, int n_streams, int sm_count, int bands, int followers,
+                                           long long out[5]) {
+    if (!out || n_filters < 1 || n_streams < 1 || sm_count < 1 || (dtype != HG_F32 && dtype != HG_F64))
+        return hg::fail(HG_ERR_INVALID, "hg_fb_debug_ru_config: bad argument");
+    hg_fb fb;
+    fb.dtype = dtype; fb.arith = arith; fb.order = 2; fb.N = n_filters; fb.S = n_streams; fb.flags = 0; fb.device = 0;
+    fb.sm_count = sm_count;
+    int dummy = 0;
+    fb.cur_env = followers ? &dummy : nullptr;
+    fb.env_mode = followers == 1 ? 1 : 2;
+    const bool vf = arith != HG_ARITH_FMA && !bands && followers != 1;
+    int W = 0, NS = 0, cps = 0;
+    size_t smem = 0;
+    if (dtype == HG_F32) { hg::fb_ru_config<float>(&fb, bands != 0, &W, &NS, &cps); smem = hg::ru::Layout<float>(W, NS, followers == 2, vf).bytes(); }
+    else { hg::fb_ru_config<double>(&fb, bands != 0, &W, &NS, &cps); smem = hg::ru::Layout<double>(W, NS, followers == 2, vf).bytes(); }
+    out[0] = W; out[1] = NS; out[2] = cps; out[3] = (long long)(W + NS + 1) * 32; out[4] = (long long)smem;
+    return HG_OK;
+}

@@ -166,6 +166,12 @@ hg_status hg_fb_check(hg_fb* fb);
  * counters of its S and R roles (waits for the y tile, for the running row, mixdown, hand-over; R's barrier waits and
  * total).  Copies [n_ctas][8] counters of the last launch (chain order).  Not part of the reference's surface. */
 hg_status hg_fb_debug_profile(hg_fb* fb, long long* counters, int n_ctas);
+/* Debug aid, host only (no CUDA call): the launch geometry the throughput-regime kernel (K1-ru) would use for a bank of
+ * n_filters x n_streams on a GPU with sm_count SMs.  followers: 0 none, 1 HG_ENV_RING, 2 HG_ENV_REPLICA.
+ * out[5] = RU warps per CTA, S warps per CTA, CTAs per stream, threads per CTA, dynamic shared memory per CTA (bytes).
+ * The ordered mixdown needs out[2] <= sm_count x CTAs per SM: tests use this to check the one-wave rule off the GPU. */
+hg_status hg_fb_debug_ru_config(int dtype, int arith, int n_filters, int n_streams, int sm_count, int bands, int followers,
+                                long long out[5]);
 
 /* ---- filter-partitioned rendering over the GPUs of one box (BASELINE configs[2]) ------------------------------ */
 /* new (nothing in the reference to match: it is single-threaded host code).  A bank of N filters is split over G
