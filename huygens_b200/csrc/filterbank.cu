@@ -422,11 +422,16 @@ static hg_status launch_k1_F(int F, const FbK1Params<T>& P, int groups, cudaStre
 }
 
 // Kernel choice.  F_out = 0: warp-specialised kernel (latency-bound regime: every CTA of 32 filters resident at
-// once, 1, 2 or 4 per SM; fp64: 1 or 2); -2: RU/S kernel (throughput regime, fused followers); 1, 2: lane kernel
-// with that many filters per thread (time-varying parameter tables, or forced).
+// once, 1, 2 or 4 per SM; fp64: 1 or 2; opt-in with HG_FB_WS_NF=2, float: CTAs of 64 filters, two chains per
+// recurrence lane, 1 or 2 per SM — measured no faster than two CTAs of 32); -2: RU/S kernel
+// (throughput regime, fused followers); 1, 2: lane kernel with that many filters per thread (time-varying
+// parameter tables, or forced).
 static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
-    const long ws_ctas = (long)((fb->N + 31) / 32) * fb->S;
-    const int max_level = fb->dtype == HG_F32 ? 2 : 1;
+    int nf = 1;
+    if (fb->dtype == HG_F32 && fb->force_ws_nf == 2) nf = 2;
+    const int per_cta = 32 * nf;
+    const long ws_ctas = (long)((fb->N + per_cta - 1) / per_cta) * fb->S;
+    const int max_level = nf == 2 ? 1 : (fb->dtype == HG_F32 ? 2 : 1);
     int level = 0;
     while (level < max_level && ws_ctas > ((long)fb->sm_count << level)) level++;
     const bool ws_fits = ws_ctas <= ((long)fb->sm_count << level);
@@ -434,8 +439,9 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     if (fb->cur_env) { *F_out = -2; return; }              // fused envelope followers live in the RU/S kernel
     if (!fb->cur_tv && (fb->force_F == -1 || (fb->force_F == 0 && ws_fits))) {
         fb->ws_level = level;
+        fb->ws_nf = nf;
         *F_out = 0;
-        *groups_out = (fb->N + 31) / 32;
+        *groups_out = (fb->N + per_cta - 1) / per_cta;
         return;
     }
     if (!fb->cur_tv && (fb->force_F == 0 || fb->force_F == -2)) { *F_out = -2; return; }
@@ -572,7 +578,7 @@ hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_
         P.tv_rows = (const T*)fb->cur_tv; P.tv_hop = fb->cur_tv_hop; P.tv_t0 = (long)t0;
         if (F == 0) {
             if (fb->ws_level > 0) HG_CUDA(cudaMemsetAsync(fb->d_sm_slot, 0, 1024 * sizeof(int), st));
-            rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, fb->ws_level, P, groups, st);
+            rc = fb_launch_exact_ws<T>(fma, d_bands != nullptr, fb->ws_level, fb->ws_nf, P, groups, st);
         }
         else if (F == -2) {
             FbEnvArgs<T> E;

@@ -73,6 +73,8 @@ hg_status hg_fb_create(hg_fb** out, int dtype, int arith, int order, int n_filte
     const size_t N = fb->N, S = fb->S;
     const char* e = getenv("HG_FB_FORCE_F");
     if (e) fb->force_F = atoi(e);
+    e = getenv("HG_FB_WS_NF");
+    if (e) fb->force_ws_nf = atoi(e);
     e = getenv("HG_FB_FORCE_CHUNKS");
     if (e) fb->force_chunks = atoi(e);
     e = getenv("HG_FB_PROF");

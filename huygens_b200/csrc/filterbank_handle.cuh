@@ -60,6 +60,8 @@ struct hg_fb {
     // last launch report
     int last_mode = 0, last_launches = 0, last_F = 0, last_ctas = 0;
     int ws_level = 0;
+    int ws_nf = 1;               // filters per recurrence lane of the last ws launch (a CTA owns 32 * ws_nf filters)
+    int force_ws_nf = 0;         // HG_FB_WS_NF (read at create): 1 or 2 forces it, 0 = by lane count
     // fused per-band envelope followers (hg_fb_process_env)
     void* d_rms_sum = nullptr;   // [S][N]
     void* d_rms_ring = nullptr;  // [S][ceil(N/32)][width][32]
@@ -118,7 +120,7 @@ template <typename T> struct FbK1Params {
 template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
 template <typename T>
-hg_status fb_launch_exact_ws(bool fma, bool bands, int level, const FbK1Params<T>& P, int groups, cudaStream_t st);
+hg_status fb_launch_exact_ws(bool fma, bool bands, int level, int nf, const FbK1Params<T>& P, int groups, cudaStream_t st);
 template <typename T> struct FbEnvArgs {
     T* env; T* rms_sum; T* rms_ring;
     int width, hop;

@@ -1,5 +1,5 @@
 // filterbank_ws_f32.cu — float instantiations of the warp-specialised exact kernel (filterbank_ws.inc).
 #include "filterbank_ws.inc"
 namespace hg {
-template hg_status fb_launch_exact_ws<float>(bool, bool, int, const FbK1Params<float>&, int, cudaStream_t);
+template hg_status fb_launch_exact_ws<float>(bool, bool, int, int, const FbK1Params<float>&, int, cudaStream_t);
 }

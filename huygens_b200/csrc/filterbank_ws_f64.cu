@@ -1,5 +1,5 @@
 // filterbank_ws_f64.cu — double instantiations of the warp-specialised exact kernel (filterbank_ws.inc).
 #include "filterbank_ws.inc"
 namespace hg {
-template hg_status fb_launch_exact_ws<double>(bool, bool, int, const FbK1Params<double>&, int, cudaStream_t);
+template hg_status fb_launch_exact_ws<double>(bool, bool, int, int, const FbK1Params<double>&, int, cudaStream_t);
 }
