@@ -50,6 +50,7 @@ SYMBOLS = [
     ("hg_fb_process_voice", _i, [_vp, _vp, _vp, _vp, _sz, _i, _vp]),
     ("hg_fb_debug_profile", _i, [_vp, _vp, _i]),
     ("hg_fb_debug_ru_config", _i, [_i, _i, _i, _i, _i, _i, _i, _vp]),
+    ("hg_fb_debug_ws_config", _i, [_i, _i, _i, _i, _i, _vp]),
     ("hg_comm_get_unique_id", _i, [_vp]),
     ("hg_comm_init_rank", _i, [C.POINTER(_vp), _i, _i, _vp, _i]),
     ("hg_comm_init_all", _i, [C.POINTER(_vp), _i, _pi]),

@@ -451,6 +451,31 @@ static void k1_config(hg_fb* fb, int* F_out, int* groups_out) {
     *groups_out = (fb->N + K1_NT * F - 1) / (K1_NT * F);
 }
 
+}  // namespace hg
+
+extern "C" hg_status hg_fb_debug_ws_config(int dtype, int n_filters, int n_streams, int sm_count, int filters_per_lane, long long out[8]) {
+    if (!out || n_filters < 1 || n_streams < 1 || sm_count < 1 || (dtype != HG_F32 && dtype != HG_F64))
+        return hg::fail(HG_ERR_INVALID, "hg_fb_debug_ws_config: bad argument");
+    hg_fb fb;
+    fb.dtype = dtype; fb.arith = HG_ARITH_STRICT; fb.order = 2; fb.N = n_filters; fb.S = n_streams; fb.flags = 0; fb.device = 0;
+    fb.sm_count = sm_count;
+    fb.force_ws_nf = filters_per_lane;
+    int F = 0, groups = 0;
+    hg::k1_config(&fb, &F, &groups);
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (F != 0) return HG_OK;                      // the bank does not fit the warp-specialised kernel: out[0] = 0
+    int tile = 0, us = 0, ys = 0;
+    long long smem = 0;
+    const bool built = dtype == HG_F32 ? hg::fb_ws_describe<float>(fb.ws_level, fb.ws_nf, &tile, &us, &ys, &smem)
+                                       : hg::fb_ws_describe<double>(fb.ws_level, fb.ws_nf, &tile, &us, &ys, &smem);
+    if (!built) return hg::fail(HG_ERR_INVALID, "hg_fb_debug_ws_config: level %d with %d filters per lane is not built", fb.ws_level, fb.ws_nf);
+    out[0] = 1; out[1] = fb.ws_level; out[2] = fb.ws_nf; out[3] = groups; out[4] = (long long)groups * n_streams;
+    out[5] = tile; out[6] = ys; out[7] = smem;
+    return HG_OK;
+}
+
+namespace hg {
+
 // rings, credits, ticket counter and watchdog flag of the ordered mixdown for `links` chain links
 static hg_status chain_reserve(hg_fb* fb, size_t links, cudaStream_t st) {
     const size_t wps = hg::dtype_size(fb->dtype) / 4;

@@ -121,6 +121,8 @@ template <typename T>
 hg_status fb_process_exact(hg_fb* fb, const T* d_in, T* d_out, T* d_bands, size_t L, cudaStream_t st);
 template <typename T>
 hg_status fb_launch_exact_ws(bool fma, bool bands, int level, int nf, const FbK1Params<T>& P, int groups, cudaStream_t st);
+template <typename T>
+bool fb_ws_describe(int level, int nf, int* tile, int* u_slots, int* y_slots, long long* smem_bytes);
 template <typename T> struct FbEnvArgs {
     T* env; T* rms_sum; T* rms_ring;
     int width, hop;

@@ -172,6 +172,13 @@ hg_status hg_fb_debug_profile(hg_fb* fb, long long* counters, int n_ctas);
  * The ordered mixdown needs out[2] <= sm_count x CTAs per SM: tests use this to check the one-wave rule off the GPU. */
 hg_status hg_fb_debug_ru_config(int dtype, int arith, int n_filters, int n_streams, int sm_count, int bands, int followers,
                                 long long out[5]);
+/* Debug aid, host only (no CUDA call): the launch geometry of the warp-specialised kernel (K1-ws) for a bank of
+ * n_filters x n_streams on a GPU with sm_count SMs.  filters_per_lane: 0 or 1 = the default CTAs of 32 filters, 2 = the
+ * opt-in CTAs of 64 filters (float; what HG_FB_WS_NF=2 selects).  out[8] = fits (0: the dispatcher picks K1-ru, the rest
+ * is 0), residency level (CTAs per SM = 1 << level), filters per lane, CTAs per stream, CTAs in total, tile length
+ * (samples), y-tile slots, dynamic shared memory per CTA (bytes).  The ordered mixdown needs all CTAs resident at once:
+ * out[4] <= sm_count << level and (out[7] + 1024) << level <= 228 KB. */
+hg_status hg_fb_debug_ws_config(int dtype, int n_filters, int n_streams, int sm_count, int filters_per_lane, long long out[8]);
 
 /* ---- filter-partitioned rendering over the GPUs of one box (BASELINE configs[2]) ------------------------------ */
 /* new (nothing in the reference to match: it is single-threaded host code).  A bank of N filters is split over G
