@@ -711,7 +711,8 @@ def main():
         tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if args.mode == "exact" and args.workload == "c2":
             traffic = {"dram_bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "samples_per_launch": tr["samples_per_launch"],
-                       "algorithmic_bytes_per_launch": 8 * tr["samples_per_launch"], "source": tr["source"], "note": tr["note"]}
+                       "algorithmic_bytes_per_launch": 8 * tr["samples_per_launch"], "source": tr["source"], "note": tr["note"],
+                       "recurrence_warp": tr.get("r_warp")}
     except Exception:
         pass
     line = {
